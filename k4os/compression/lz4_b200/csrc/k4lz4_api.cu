@@ -1,0 +1,550 @@
+// k4lz4_api.cu -- the C ABI of libk4lz4 (include/k4lz4.h): argument handling, the
+// device-resident launch path, the host-buffer staging path (chunked, double-buffered,
+// NCCL-free multi-GPU split of the block list) and the synthetic workload generator.
+//
+// There is deliberately NO CPU codec in this library: without a usable CUDA device every
+// compute entry point fails with K4LZ4_E_NODEVICE.
+#include "../../../../include/k4lz4.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+#include "decode_generic.cuh"
+#include "decode_tile.cuh"
+#include "encode_generic.cuh"
+#include "pickle.cuh"
+#include "synth.cuh"
+#include "copy_blocks.cuh"
+
+namespace {
+
+std::atomic<int64_t> g_launches{0};
+thread_local std::string t_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    t_err = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                         \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return fail(K4LZ4_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));      \
+    } while (0)
+
+int device_count_cached() {
+    static int n = [] {
+        int c = 0;
+        cudaError_t e = cudaGetDeviceCount(&c);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+        return c;
+    }();
+    return n;
+}
+
+// ---- kernel launchers (device pointers) ---------------------------------------------------
+
+enum Op { OP_ENCODE = 0, OP_DECODE = 1, OP_PICKLE = 2, OP_UNPICKLE = 3, OP_USIZE = 4 };
+
+std::once_flag g_attr_once[64];
+
+void set_func_attrs(int dev) {
+    if (dev < 0 || dev >= 64) return;
+    std::call_once(g_attr_once[dev], [] {
+        cudaFuncSetAttribute(k4::encode_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             k4::ENC_WARPS_PER_CTA * k4::ENC_TABLE_BYTES);
+        cudaFuncSetAttribute(k4::pickle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             k4::ENC_WARPS_PER_CTA * k4::ENC_TABLE_BYTES);
+        k4::decode_tile_set_attrs();
+    });
+}
+
+struct DevArgs {
+    const uint8_t* srcBase; const int64_t* srcOff; const int32_t* srcLen;
+    uint8_t* dstBase; const int64_t* dstOff; const int32_t* dstCap;
+    int32_t* outLen; int n; int level;
+};
+
+cudaError_t launch_op(Op op, const DevArgs& a, cudaStream_t st) {
+    if (a.n <= 0) return cudaSuccess;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    set_func_attrs(dev);
+    switch (op) {
+    case OP_ENCODE: {
+        const int ctas = (a.n + k4::ENC_WARPS_PER_CTA - 1) / k4::ENC_WARPS_PER_CTA;
+        k4::encode_generic_kernel<<<ctas, k4::ENC_WARPS_PER_CTA * 32,
+                                    k4::ENC_WARPS_PER_CTA * k4::ENC_TABLE_BYTES, st>>>(
+            a.srcBase, a.srcOff, a.srcLen, a.dstBase, a.dstOff, a.dstCap, a.outLen, a.n, a.level, 0);
+        g_launches++;
+        break;
+    }
+    case OP_DECODE:
+        g_launches += k4::decode_tile_launch(a.srcBase, a.srcOff, a.srcLen, a.dstBase, a.dstOff,
+                                             a.dstCap, a.outLen, a.n, st);
+        break;
+    case OP_PICKLE: {
+        const int ctas = (a.n + k4::ENC_WARPS_PER_CTA - 1) / k4::ENC_WARPS_PER_CTA;
+        k4::pickle_kernel<<<ctas, k4::ENC_WARPS_PER_CTA * 32,
+                            k4::ENC_WARPS_PER_CTA * k4::ENC_TABLE_BYTES, st>>>(
+            a.srcBase, a.srcOff, a.srcLen, a.dstBase, a.dstOff, a.outLen, a.n, a.level);
+        g_launches++;
+        break;
+    }
+    case OP_UNPICKLE: {
+        const int ctas = (a.n + 3) / 4;
+        k4::unpickle_kernel<<<ctas, 128, 0, st>>>(a.srcBase, a.srcOff, a.srcLen, a.dstBase, a.dstOff,
+                                                  a.dstCap, a.outLen, a.n);
+        g_launches++;
+        break;
+    }
+    case OP_USIZE: {
+        const int ctas = (a.n + 255) / 256;
+        k4::unpickled_size_kernel<<<ctas, 256, 0, st>>>(a.srcBase, a.srcOff, a.srcLen, a.outLen, a.n);
+        g_launches++;
+        break;
+    }
+    }
+    return cudaGetLastError();
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (dev >= 0) {
+            cudaGetDevice(&prev);
+            if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess; else prev = -1;
+        }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int run_device(Op op, const DevArgs& a, void* stream, int device) {
+    if (device_count_cached() <= 0) return fail(K4LZ4_E_NODEVICE, "no CUDA device available");
+    if (a.n < 0) return fail(K4LZ4_E_ARG, "negative block count");
+    if (a.n == 0) return K4LZ4_OK;
+    if (!a.srcBase || !a.srcOff || !a.srcLen || !a.outLen) return fail(K4LZ4_E_ARG, "null pointer argument");
+    if (op != OP_USIZE && (!a.dstBase || !a.dstOff)) return fail(K4LZ4_E_ARG, "null pointer argument");
+    if ((op == OP_ENCODE || op == OP_DECODE || op == OP_UNPICKLE) && !a.dstCap)
+        return fail(K4LZ4_E_ARG, "null pointer argument");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(K4LZ4_E_CUDA, "cudaSetDevice(%d) failed", device);
+    CU_TRY(launch_op(op, a, (cudaStream_t)stream));
+    return K4LZ4_OK;
+}
+
+// ---- host-buffer path ----------------------------------------------------------------------
+
+struct DBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, n); want = n; }
+        if (e == cudaSuccess) cap = want; else p = nullptr;
+        return e;
+    }
+};
+struct HBuf {   // pinned host
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 4096;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) { e = cudaHostAlloc(&p, n, cudaHostAllocDefault); want = n; }
+        if (e == cudaSuccess) cap = want; else p = nullptr;
+        return e;
+    }
+};
+
+struct Slot {          // one in-flight chunk
+    cudaStream_t stream = nullptr;
+    DBuf dSrc, dDst, dMeta;
+    HBuf hSrc, hDst, hMeta;
+    // description of the chunk that is in flight
+    int64_t b0 = 0, b1 = 0;           // block range
+    int64_t dLo = 0;                  // dst extent origin (direct mode) or 0 (packed mode)
+    bool dstPacked = false;
+    std::vector<int64_t> packedDstOff;
+    bool busy = false;
+};
+
+struct DevCtx {
+    int dev = -1;
+    std::mutex mu;
+    Slot slot[2];
+    bool init = false;
+};
+
+DevCtx* get_ctx(int dev) {
+    static std::mutex m;
+    static std::vector<std::unique_ptr<DevCtx>> ctxs;
+    std::lock_guard<std::mutex> lk(m);
+    if ((int)ctxs.size() <= dev) ctxs.resize(dev + 1);
+    if (!ctxs[dev]) { ctxs[dev].reset(new DevCtx()); ctxs[dev]->dev = dev; }
+    return ctxs[dev].get();
+}
+
+struct HostArgs {
+    const uint8_t* srcBase; const int64_t* srcOff; const int32_t* srcLen;
+    uint8_t* dstBase; const int64_t* dstOff; const int32_t* dstCap;
+    int32_t* outLen; int level;
+};
+
+inline int64_t dst_room(Op op, const HostArgs& a, int64_t i) {
+    switch (op) {
+    case OP_PICKLE: return a.srcLen[i] <= 0 ? 0 : (int64_t)a.srcLen[i] + 1;
+    case OP_USIZE: return 0;
+    default: return a.dstCap[i] < 0 ? 0 : a.dstCap[i];
+    }
+}
+inline int64_t src_size(const HostArgs& a, int64_t i) { return a.srcLen[i] < 0 ? 0 : a.srcLen[i]; }
+
+void parallel_for_blocks(int64_t b0, int64_t b1, int64_t bytesHint, const std::function<void(int64_t, int64_t)>& fn);
+
+constexpr int64_t CHUNK_BYTES = 192ll << 20;   // src + dst payload per in-flight chunk
+
+// Copies every produced byte of chunk [b0,b1) from the pinned staging buffer into the
+// caller's destination; bytes at index >= outLen[i] are never touched.
+void scatter_chunk(Op op, const HostArgs& a, Slot& s) {
+    if (op == OP_USIZE) return;
+    const uint8_t* stage = (const uint8_t*)s.hDst.p;
+    int64_t total = 0;
+    for (int64_t i = s.b0; i < s.b1; i++) total += std::max<int32_t>(a.outLen[i], 0);
+    parallel_for_blocks(s.b0, s.b1, total, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; i++) {
+            const int32_t r = a.outLen[i];
+            if (r <= 0) continue;
+            const int64_t off = s.dstPacked ? s.packedDstOff[i - s.b0] : a.dstOff[i] - s.dLo;
+            memcpy(a.dstBase + a.dstOff[i], stage + off, (size_t)r);
+        }
+    });
+}
+
+int finish_slot(Op op, const HostArgs& a, Slot& s) {
+    if (!s.busy) return K4LZ4_OK;
+    s.busy = false;
+    CU_TRY(cudaStreamSynchronize(s.stream));
+    memcpy(a.outLen + s.b0, (const int32_t*)s.hMeta.p, sizeof(int32_t) * (size_t)(s.b1 - s.b0));
+    scatter_chunk(op, a, s);
+    return K4LZ4_OK;
+}
+
+int enqueue_chunk(Op op, const HostArgs& a, Slot& s, int64_t b0, int64_t b1) {
+    const int64_t nb = b1 - b0;
+    s.b0 = b0; s.b1 = b1;
+    // extents
+    int64_t sLo = INT64_MAX, sHi = INT64_MIN, dLo = INT64_MAX, dHi = INT64_MIN, sSum = 0, dSum = 0;
+    for (int64_t i = b0; i < b1; i++) {
+        const int64_t sl = src_size(a, i), dl = dst_room(op, a, i);
+        if (sl > 0) { sLo = std::min(sLo, a.srcOff[i]); sHi = std::max(sHi, a.srcOff[i] + sl); sSum += sl; }
+        if (dl > 0) { dLo = std::min(dLo, a.dstOff[i]); dHi = std::max(dHi, a.dstOff[i] + dl); dSum += dl; }
+    }
+    if (sSum == 0) { sLo = 0; sHi = 0; }
+    if (dSum == 0) { dLo = 0; dHi = 0; }
+    const bool srcPacked = (sHi - sLo) > sSum + sSum / 4 + 65536;
+    const bool dstPacked = (dHi - dLo) > dSum + dSum / 4 + 65536;
+    s.dstPacked = dstPacked;
+    s.dLo = dLo;
+
+    // meta layout (device): srcOff[nb] dstOff[nb] (int64) | srcLen[nb] dstCap[nb] outLen[nb] (int32)
+    const size_t metaBytes = (size_t)nb * (8 + 8 + 4 + 4 + 4);
+    CU_TRY(s.dMeta.ensure(metaBytes));
+    CU_TRY(s.hMeta.ensure(metaBytes));
+    int64_t* hSrcOff = (int64_t*)s.hMeta.p;
+    int64_t* hDstOff = hSrcOff + nb;
+    int32_t* hSrcLen = (int32_t*)(hDstOff + nb);
+    int32_t* hDstCap = hSrcLen + nb;
+    // (outLen comes back into the front of hMeta after the kernel; see below)
+    int64_t* dSrcOff = (int64_t*)s.dMeta.p;
+    int64_t* dDstOff = dSrcOff + nb;
+    int32_t* dSrcLen = (int32_t*)(dDstOff + nb);
+    int32_t* dDstCap = dSrcLen + nb;
+    int32_t* dOutLen = dDstCap + nb;
+
+    const int64_t srcBytes = srcPacked ? sSum : (sHi - sLo);
+    const int64_t dstBytes = dstPacked ? dSum : (dHi - dLo);
+    CU_TRY(s.dSrc.ensure((size_t)srcBytes + 16));
+    if (op != OP_USIZE) {
+        CU_TRY(s.dDst.ensure((size_t)dstBytes + 16));
+        CU_TRY(s.hDst.ensure((size_t)dstBytes + 16));
+    }
+    if (dstPacked) s.packedDstOff.resize((size_t)nb);
+
+    int64_t sp = 0, dp = 0;
+    if (srcPacked) CU_TRY(s.hSrc.ensure((size_t)sSum + 16));
+    for (int64_t i = b0; i < b1; i++) {
+        const int64_t k = i - b0;
+        const int64_t sl = src_size(a, i), dl = dst_room(op, a, i);
+        hSrcLen[k] = a.srcLen[i];
+        hDstCap[k] = (op == OP_PICKLE || op == OP_USIZE) ? 0 : a.dstCap[i];
+        if (srcPacked) {
+            hSrcOff[k] = sp;
+            if (sl > 0) memcpy((uint8_t*)s.hSrc.p + sp, a.srcBase + a.srcOff[i], (size_t)sl);
+            sp += sl;
+        } else {
+            hSrcOff[k] = sl > 0 ? a.srcOff[i] - sLo : 0;
+        }
+        if (dstPacked) { hDstOff[k] = dp; s.packedDstOff[(size_t)k] = dp; dp += dl; }
+        else hDstOff[k] = dl > 0 ? a.dstOff[i] - dLo : 0;
+    }
+
+    cudaStream_t st = s.stream;
+    if (srcBytes > 0)
+        CU_TRY(cudaMemcpyAsync(s.dSrc.p, srcPacked ? (const void*)s.hSrc.p : (const void*)(a.srcBase + sLo),
+                               (size_t)srcBytes, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(s.dMeta.p, s.hMeta.p, (size_t)nb * 24, cudaMemcpyHostToDevice, st));
+    DevArgs d{(const uint8_t*)s.dSrc.p, dSrcOff, dSrcLen, (uint8_t*)s.dDst.p, dDstOff, dDstCap,
+              dOutLen, (int)nb, a.level};
+    CU_TRY(launch_op(op, d, st));
+    if (op != OP_USIZE && dstBytes > 0)
+        CU_TRY(cudaMemcpyAsync(s.hDst.p, s.dDst.p, (size_t)dstBytes, cudaMemcpyDeviceToHost, st));
+    // outLen lands at the front of hMeta (offset arrays there are no longer needed once the
+    // H2D above has been issued *and completed*; stream order guarantees that)
+    CU_TRY(cudaMemcpyAsync(s.hMeta.p, dOutLen, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+    s.busy = true;
+    return K4LZ4_OK;
+}
+
+// One device, blocks [b0, b1): chunked + double-buffered (H2D/kernel/D2H of chunk c overlap
+// the host-side scatter of chunk c-1 and the copies of chunk c+1 on the other stream).
+int run_host_slice(Op op, const HostArgs& a, int64_t b0, int64_t b1, int dev) {
+    if (b1 <= b0) return K4LZ4_OK;
+    DevCtx* ctx = get_ctx(dev);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(dev);
+    if (!g.ok) return fail(K4LZ4_E_CUDA, "cudaSetDevice(%d) failed", dev);
+    if (!ctx->init) {
+        for (auto& s : ctx->slot) CU_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        ctx->init = true;
+    }
+    int rc = K4LZ4_OK;
+    int64_t i = b0;
+    int c = 0;
+    while (i < b1) {
+        int64_t bytes = 0, j = i;
+        while (j < b1 && (j == i || bytes + src_size(a, j) + dst_room(op, a, j) <= CHUNK_BYTES)) {
+            bytes += src_size(a, j) + dst_room(op, a, j);
+            j++;
+        }
+        Slot& s = ctx->slot[c & 1];
+        if ((rc = finish_slot(op, a, s)) != K4LZ4_OK) break;
+        if ((rc = enqueue_chunk(op, a, s, i, j)) != K4LZ4_OK) break;
+        i = j; c++;
+    }
+    // drain in issue order
+    int rc2 = finish_slot(op, a, ctx->slot[c & 1]);
+    int rc3 = finish_slot(op, a, ctx->slot[(c + 1) & 1]);
+    if (rc != K4LZ4_OK) { for (auto& s : ctx->slot) { s.busy = false; } cudaDeviceSynchronize(); return rc; }
+    return rc2 != K4LZ4_OK ? rc2 : rc3;
+}
+
+void parallel_for_blocks(int64_t b0, int64_t b1, int64_t bytesHint,
+                         const std::function<void(int64_t, int64_t)>& fn) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int T = (int)std::min<unsigned>(hw ? hw : 1, 16);
+    if (bytesHint < (8 << 20) || b1 - b0 < 2 * T) T = 1;
+    if (T <= 1) { fn(b0, b1); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++) {
+        int64_t lo = b0 + (b1 - b0) * t / T, hi = b0 + (b1 - b0) * (t + 1) / T;
+        th.emplace_back([=, &fn] { fn(lo, hi); });
+    }
+    for (auto& t : th) t.join();
+}
+
+int run_host(Op op, const HostArgs& a, int64_t n, int device) {
+    const int ndev = device_count_cached();
+    if (ndev <= 0) return fail(K4LZ4_E_NODEVICE, "no CUDA device available");
+    if (n < 0) return fail(K4LZ4_E_ARG, "negative block count");
+    if (n == 0) return K4LZ4_OK;
+    if (!a.srcBase || !a.srcOff || !a.srcLen || !a.outLen) return fail(K4LZ4_E_ARG, "null pointer argument");
+    if (op != OP_USIZE && (!a.dstBase || !a.dstOff)) return fail(K4LZ4_E_ARG, "null pointer argument");
+    if ((op == OP_ENCODE || op == OP_DECODE || op == OP_UNPICKLE) && !a.dstCap)
+        return fail(K4LZ4_E_ARG, "null pointer argument");
+    if (device >= ndev) return fail(K4LZ4_E_ARG, "device %d out of range (%d visible)", device, ndev);
+    if (device >= 0 || ndev == 1) return run_host_slice(op, a, 0, n, device >= 0 ? device : 0);
+
+    // K4LZ4_ALL_DEVICES: contiguous split balanced by bytes, one host thread per GPU
+    std::vector<int64_t> cut(ndev + 1, n);
+    cut[0] = 0;
+    int64_t total = 0;
+    for (int64_t i = 0; i < n; i++) total += src_size(a, i) + dst_room(op, a, i) + 64;
+    int64_t acc = 0; int g = 1;
+    for (int64_t i = 0; i < n && g < ndev; i++) {
+        acc += src_size(a, i) + dst_room(op, a, i) + 64;
+        while (g < ndev && acc >= total * g / ndev) cut[g++] = i + 1;
+    }
+    std::vector<int> rcs(ndev, K4LZ4_OK);
+    std::vector<std::string> errs(ndev);
+    std::vector<std::thread> th;
+    for (int d = 0; d < ndev; d++)
+        th.emplace_back([&, d] {
+            rcs[d] = run_host_slice(op, a, cut[d], cut[d + 1], d);
+            if (rcs[d] != K4LZ4_OK) errs[d] = t_err;
+        });
+    for (auto& t : th) t.join();
+    for (int d = 0; d < ndev; d++) if (rcs[d] != K4LZ4_OK) { t_err = errs[d]; return rcs[d]; }
+    return K4LZ4_OK;
+}
+
+int run(Op op, const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen, uint8_t* dstBase,
+        const int64_t* dstOff, const int32_t* dstCap, int32_t* outLen, int64_t n, int level,
+        int memKind, void* stream, int device) {
+    if (memKind == K4LZ4_MEM_DEVICE) {
+        if (n > INT32_MAX) return fail(K4LZ4_E_ARG, "too many blocks");
+        DevArgs d{srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, (int)n, level};
+        return run_device(op, d, stream, device);
+    }
+    if (memKind == K4LZ4_MEM_HOST) {
+        HostArgs h{srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, level};
+        return run_host(op, h, n, device);
+    }
+    return fail(K4LZ4_E_ARG, "unknown memKind %d", memKind);
+}
+
+}  // namespace
+
+// ---- exported C ABI ------------------------------------------------------------------------
+
+extern "C" {
+
+int32_t k4lz4_codec_version(void) { return 192; }
+int32_t k4lz4_device_count(void) { return device_count_cached(); }
+const char* k4lz4_last_error(void) { return t_err.c_str(); }
+int64_t k4lz4_launch_count(void) { return g_launches.load(); }
+
+int32_t k4lz4_max_output_size(int32_t length) { return k4::max_output_size(length); }
+int32_t k4lz4_pickle_bound(int32_t length) { return length <= 0 ? 0 : length + 1; }
+
+int32_t k4lz4_encode(const uint8_t* src, int32_t srcLen, uint8_t* dst, int32_t dstCap, int32_t level) {
+    if (srcLen <= 0) return 0;                       // LZ4Codec.cs:45-46
+    if (level >= 3) return K4LZ4_R_DELEGATE;
+    if (!src || (!dst && dstCap > 0)) return fail(K4LZ4_E_ARG, "null pointer argument");
+    if (dstCap <= 0) return -1;                      // nothing fits in an empty target
+    int64_t so = 0, dof = 0; int32_t out = -1;
+    int rc = run(OP_ENCODE, src, &so, &srcLen, dst, &dof, &dstCap, &out, 1, level, K4LZ4_MEM_HOST, nullptr, 0);
+    return rc != K4LZ4_OK ? rc : out;
+}
+
+int32_t k4lz4_decode(const uint8_t* src, int32_t srcLen, uint8_t* dst, int32_t dstCap) {
+    if (srcLen <= 0) return 0;                       // LZ4Codec.cs:108-109
+    if (!src || (!dst && dstCap > 0)) return fail(K4LZ4_E_ARG, "null pointer argument");
+    if (dstCap <= 0) return -1;                      // LL64.dec.cs:162-168 gives 0 or -1 => -1
+    int64_t so = 0, dof = 0; int32_t out = -1;
+    int rc = run(OP_DECODE, src, &so, &srcLen, dst, &dof, &dstCap, &out, 1, 0, K4LZ4_MEM_HOST, nullptr, 0);
+    return rc != K4LZ4_OK ? rc : out;
+}
+
+int32_t k4lz4_encode_batch(const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen,
+                           uint8_t* dstBase, const int64_t* dstOff, const int32_t* dstCap,
+                           int32_t* outLen, int32_t nBlocks, int32_t level, int32_t memKind,
+                           void* cudaStream, int32_t device) {
+    return run(OP_ENCODE, srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, nBlocks, level,
+               memKind, cudaStream, device);
+}
+
+int32_t k4lz4_decode_batch(const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen,
+                           uint8_t* dstBase, const int64_t* dstOff, const int32_t* dstCap,
+                           int32_t* outLen, int32_t nBlocks, int32_t memKind, void* cudaStream,
+                           int32_t device) {
+    return run(OP_DECODE, srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, nBlocks, 0,
+               memKind, cudaStream, device);
+}
+
+int32_t k4lz4_pickle_batch(const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen,
+                           uint8_t* dstBase, const int64_t* dstOff, int32_t* outLen,
+                           int32_t nMessages, int32_t level, int32_t memKind, void* cudaStream,
+                           int32_t device) {
+    return run(OP_PICKLE, srcBase, srcOff, srcLen, dstBase, dstOff, nullptr, outLen, nMessages, level,
+               memKind, cudaStream, device);
+}
+
+int32_t k4lz4_unpickled_size_batch(const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen,
+                                   int32_t* outSize, int32_t nMessages, int32_t memKind,
+                                   void* cudaStream, int32_t device) {
+    return run(OP_USIZE, srcBase, srcOff, srcLen, nullptr, nullptr, nullptr, outSize, nMessages, 0,
+               memKind, cudaStream, device);
+}
+
+int32_t k4lz4_unpickle_batch(const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen,
+                             uint8_t* dstBase, const int64_t* dstOff, const int32_t* dstLen,
+                             int32_t* outLen, int32_t nMessages, int32_t memKind, void* cudaStream,
+                             int32_t device) {
+    return run(OP_UNPICKLE, srcBase, srcOff, srcLen, dstBase, dstOff, dstLen, outLen, nMessages, 0,
+               memKind, cudaStream, device);
+}
+
+int32_t k4lz4_synth_host(uint8_t* base, int64_t nBlocks, int32_t blockSize, int32_t matchPermille,
+                         uint64_t seed, int64_t firstBlock) {
+    if (!base || nBlocks < 0 || blockSize <= 0) return fail(K4LZ4_E_ARG, "bad synth arguments");
+    unsigned hw = std::thread::hardware_concurrency();
+    int T = (int)std::min<int64_t>(std::min<unsigned>(hw ? hw : 1, 64), std::max<int64_t>(nBlocks, 1));
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++)
+        th.emplace_back([=] {
+            for (int64_t b = nBlocks * t / T; b < nBlocks * (t + 1) / T; b++)
+                k4::synth_block(base + b * (int64_t)blockSize, blockSize, (uint32_t)matchPermille, seed,
+                                (uint64_t)(firstBlock + b));
+        });
+    for (auto& t : th) t.join();
+    return K4LZ4_OK;
+}
+
+int32_t k4lz4_synth_device(uint8_t* base, int64_t nBlocks, int32_t blockSize, int32_t matchPermille,
+                           uint64_t seed, int64_t firstBlock, void* cudaStream, int32_t device) {
+    if (device_count_cached() <= 0) return fail(K4LZ4_E_NODEVICE, "no CUDA device available");
+    if (!base || nBlocks < 0 || blockSize <= 0) return fail(K4LZ4_E_ARG, "bad synth arguments");
+    if (nBlocks == 0) return K4LZ4_OK;
+    DeviceGuard g(device);
+    if (!g.ok) return fail(K4LZ4_E_CUDA, "cudaSetDevice(%d) failed", device);
+    const int threads = 64;
+    const long long ctas = (nBlocks + threads - 1) / threads;
+    k4::synth_kernel<<<(unsigned)ctas, threads, 0, (cudaStream_t)cudaStream>>>(
+        base, nBlocks, blockSize, (uint32_t)matchPermille, seed, firstBlock);
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+    return K4LZ4_OK;
+}
+
+int32_t k4lz4_copy_blocks_device(const uint8_t* srcBase, const int64_t* srcOff, uint8_t* dstBase,
+                                 const int64_t* dstOff, const int32_t* len, int32_t nBlocks,
+                                 void* cudaStream, int32_t device) {
+    if (device_count_cached() <= 0) return fail(K4LZ4_E_NODEVICE, "no CUDA device available");
+    if (nBlocks < 0 || !srcBase || !srcOff || !dstBase || !dstOff || !len)
+        return fail(K4LZ4_E_ARG, "bad copy_blocks arguments");
+    if (nBlocks == 0) return K4LZ4_OK;
+    DeviceGuard g(device);
+    if (!g.ok) return fail(K4LZ4_E_CUDA, "cudaSetDevice(%d) failed", device);
+    k4::copy_blocks_kernel<<<nBlocks, 256, 0, (cudaStream_t)cudaStream>>>(srcBase, srcOff, dstBase,
+                                                                         dstOff, len, nBlocks);
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+    return K4LZ4_OK;
+}
+
+}  // extern "C"

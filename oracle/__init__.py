@@ -1,0 +1,182 @@
+"""oracle -- CPU checker for the K4os LZ4 block hot path (TEST INFRASTRUCTURE ONLY).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` legs may import this package.  The product package
+(``k4os.compression.lz4_b200``) never does.
+
+Two engines are exposed through the same thin ctypes surface:
+
+* ``port``  -- ``oracle/_build/libk4oracle.so``: the C restatement in
+  ``k4lz4_oracle.c`` (each function cites the reference file:line it follows);
+* ``ref``   -- ``oracle/_ref/libk4ref.so``: the reference's own upstream C engine
+  (``/root/reference/orig/lib/lz4.c``) compiled as-is by ``oracle/Makefile``.  It exists
+  only where it was built (this container) or shipped prebuilt (the GPU box).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_SO = os.path.join(_HERE, "_build", "libk4oracle.so")
+REF_SO = os.path.join(_HERE, "_ref", "libk4ref.so")
+PICKLE_CORRUPT = -1000
+
+_u8p = C.POINTER(C.c_uint8)
+
+
+def build(quiet: bool = True) -> None:
+    """Compile the restatement and (when /root/reference is present) the reference engine."""
+    out = subprocess.run(["make", "-C", _HERE], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + out.stdout + out.stderr)
+    if not quiet:
+        print(out.stdout)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_u8p)
+
+
+def _as_u8(b) -> np.ndarray:
+    if isinstance(b, np.ndarray):
+        return np.ascontiguousarray(b, dtype=np.uint8)
+    return np.frombuffer(bytes(b), dtype=np.uint8)
+
+
+class _Harness:
+    def __init__(self, lib):
+        self._lib = lib
+        lib.k4h_run_batch.restype = C.c_double
+        lib.k4h_run_batch.argtypes = [
+            C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+            C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+
+    def run_batch(self, mode, src, src_off, src_len, dst, dst_off, dst_cap, out_len, threads):
+        """mode 0 = encode, 1 = decode.  All arrays numpy (u8 / i64 / i32).  Returns seconds."""
+        n = int(src_len.shape[0])
+        return float(self._lib.k4h_run_batch(
+            mode, src.ctypes.data, src_off.ctypes.data, src_len.ctypes.data,
+            dst.ctypes.data, dst_off.ctypes.data, dst_cap.ctypes.data,
+            out_len.ctypes.data, n, int(threads)))
+
+
+class Port(_Harness):
+    """The C restatement (k4lz4_oracle.c)."""
+    kind = "port"
+
+    def __init__(self):
+        if not os.path.exists(PORT_SO):
+            build()
+        lib = C.CDLL(PORT_SO)
+        super().__init__(lib)
+        lib.k4o_compress_fast.argtypes = [_u8p, C.c_int, _u8p, C.c_int, C.c_int]
+        lib.k4o_decompress_safe.argtypes = [_u8p, C.c_int, _u8p, C.c_int]
+        lib.k4o_codec_encode.argtypes = [_u8p, C.c_int, _u8p, C.c_int, C.c_int, C.c_int]
+        lib.k4o_codec_decode.argtypes = [_u8p, C.c_int, _u8p, C.c_int]
+        lib.k4o_pickle.argtypes = [_u8p, C.c_int, _u8p, _u8p, C.c_int]
+        lib.k4o_unpickled_size.argtypes = [_u8p, C.c_int]
+        lib.k4o_unpickle.argtypes = [_u8p, C.c_int, _u8p, C.c_int]
+
+    def max_output_size(self, n: int) -> int:
+        return int(self._lib.k4o_max_output_size(n))
+
+    def encode(self, src, cap: int | None = None, level: int = 0, enforce32: bool = False):
+        """LZ4Codec.Encode semantics -> (ret, bytes)."""
+        s = _as_u8(src)
+        n = int(s.shape[0])
+        if cap is None:
+            cap = self.max_output_size(n)
+        d = np.zeros(max(cap, 1), dtype=np.uint8)
+        r = int(self._lib.k4o_codec_encode(_ptr(s), n, _ptr(d), cap, level, int(enforce32)))
+        return r, (d[:r].tobytes() if r > 0 else b"")
+
+    def decode(self, src, cap: int):
+        """LZ4Codec.Decode semantics -> (ret, bytes)."""
+        s = _as_u8(src)
+        d = np.zeros(max(cap, 1), dtype=np.uint8)
+        r = int(self._lib.k4o_codec_decode(_ptr(s), int(s.shape[0]), _ptr(d), cap))
+        return r, (d[:r].tobytes() if r > 0 else b"")
+
+    def decompress_safe_raw(self, src, cap: int) -> int:
+        """Engine-level return value (negative error position), LL64.dec.cs:465."""
+        s = _as_u8(src)
+        d = np.zeros(max(cap, 1), dtype=np.uint8)
+        return int(self._lib.k4o_decompress_safe(_ptr(s), int(s.shape[0]), _ptr(d), cap))
+
+    def pickle(self, src, level: int = 0) -> bytes:
+        s = _as_u8(src)
+        n = int(s.shape[0])
+        if n == 0:
+            return b""
+        d = np.zeros(n + 1, dtype=np.uint8)
+        scratch = np.zeros(max(n, 1024), dtype=np.uint8)
+        r = int(self._lib.k4o_pickle(_ptr(s), n, _ptr(d), _ptr(scratch), level))
+        return d[:r].tobytes()
+
+    def unpickled_size(self, src) -> int:
+        s = _as_u8(src)
+        return int(self._lib.k4o_unpickled_size(_ptr(s), int(s.shape[0])))
+
+    def unpickle(self, src):
+        """-> (ret, bytes); ret == PICKLE_CORRUPT where the reference throws."""
+        s = _as_u8(src)
+        n = int(s.shape[0])
+        if n == 0:
+            return 0, b""
+        size = self.unpickled_size(s)
+        if size < 0:
+            return PICKLE_CORRUPT, b""
+        d = np.zeros(max(size, 1), dtype=np.uint8)
+        r = int(self._lib.k4o_unpickle(_ptr(s), n, _ptr(d), size))
+        return r, (d[:r].tobytes() if r > 0 else b"")
+
+
+class Ref(_Harness):
+    """The reference's own upstream C engine (orig/lib/lz4.c), LZ4Codec post-processing applied."""
+    kind = "reference"
+
+    def __init__(self):
+        if not os.path.exists(REF_SO):
+            raise FileNotFoundError(REF_SO)
+        lib = C.CDLL(REF_SO)
+        super().__init__(lib)
+        lib.k4ref_compress_fast.argtypes = [_u8p, C.c_int, _u8p, C.c_int]
+        lib.k4ref_decompress_safe.argtypes = [_u8p, C.c_int, _u8p, C.c_int]
+
+    def version(self) -> int:
+        return int(self._lib.k4ref_version())
+
+    def encode(self, src, cap: int | None = None):
+        s = _as_u8(src)
+        n = int(s.shape[0])
+        if n <= 0:
+            return 0, b""
+        if cap is None:
+            cap = n + n // 255 + 16
+        d = np.zeros(max(cap, 1), dtype=np.uint8)
+        r = int(self._lib.k4ref_compress_fast(_ptr(s), n, _ptr(d), cap))
+        r = -1 if r <= 0 else r
+        return r, (d[:r].tobytes() if r > 0 else b"")
+
+    def decode(self, src, cap: int):
+        s = _as_u8(src)
+        n = int(s.shape[0])
+        if n <= 0:
+            return 0, b""
+        d = np.zeros(max(cap, 1), dtype=np.uint8)
+        r = int(self._lib.k4ref_decompress_safe(_ptr(s), n, _ptr(d), cap))
+        r = -1 if r <= 0 else r
+        return r, (d[:r].tobytes() if r > 0 else b"")
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def best():
+    """The strongest checker available here: the compiled reference if present, else the port."""
+    return Ref() if have_ref() else Port()

@@ -1,0 +1,153 @@
+"""Pins the oracle (oracle/k4lz4_oracle.c) before anything trusts it.  CPU only.
+
+* against the reference's own golden decode vector (assets/issue64 via Issue64.cs:16-55),
+* against committed known-answer encode rows made by the reference's upstream C engine
+  (tests/golden/make_golden.py; style of ChecksumBlockTests.cs:185-216),
+* differentially against that engine itself (oracle/_ref) where it is present, including
+  malformed streams, and
+* the reference's roundtrip / boundary tests (BlockRoundtripTests.cs:44-125) and pickler
+  tests (PicklingTests.cs:11-172) restated on the oracle.
+"""
+import base64
+import hashlib
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from tests import inputs
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_issue64_golden_decode(port):
+    comp = open(os.path.join(G, "issue64_block0.lz4"), "rb").read()
+    expect = open(os.path.join(G, "issue64_block0.bin"), "rb").read()
+    assert len(comp) == 14505 and len(expect) == 65536
+    r, out = port.decode(comp, 65536)
+    assert r == 65536 and out == expect
+    r2, out2 = port.decode(comp, 2 * 65536)        # larger target is fine (BlockRoundtripTests.cs:56-59)
+    assert r2 == 65536 and out2 == expect
+    assert port.decode(comp, 65535)[0] == -1       # does not fit
+
+
+def test_golden_encode_rows(port):
+    rows = json.load(open(os.path.join(G, "encode_rows.json")))["rows"]
+    assert len(rows) >= 300
+    for row in rows:
+        data = inputs.gen(row["kind"], row["size"], row["seed"])
+        r, c = port.encode(data)
+        assert r == row["len"], row
+        assert zlib.adler32(c) & 0xFFFFFFFF == row["adler32"], row
+        assert hashlib.sha256(c).hexdigest() == row["sha256"], row
+        assert base64.b64encode(c[:60]).decode() == row["head60"], row
+        for cap, expect in row["limited"]:
+            assert port.encode(data, cap)[0] == expect, (row["kind"], row["size"], cap)
+        # roundtrip through the oracle decoder, exact and oversized targets
+        assert port.decode(c, row["size"]) == (row["size"], data)
+        assert port.decode(c, row["size"] + 100)[0] == row["size"]
+
+
+def test_port_equals_reference_engine(port, ref):
+    for name, data in inputs.corpus(sizes=inputs.THRESHOLD_SIZES + inputs.BIG_SIZES):
+        a, b = ref.encode(data), port.encode(data)
+        assert a == b, name
+        n = len(data)
+        for cap in {n, n + 1, n - 1, 2 * n, max(n - 13, 0)}:
+            x, y = ref.decode(a[1], cap), port.decode(a[1], cap)
+            assert x[0] == y[0], (name, cap)
+            if x[0] > 0:
+                assert x[1] == y[1]
+
+
+def test_malformed_decode_matches_reference_engine(port, ref):
+    rng = np.random.default_rng(7)
+    checked = 0
+    for it in range(6000):
+        n = int(rng.choice([20, 50, 100, 300, 1000, 5000]))
+        kind = ["text2", "lowent", "runs", "random", "lorem"][it % 5]
+        data = inputs.gen(kind, n, it)
+        c = inputs.mutate(port.encode(data)[1], rng)
+        cap = int(rng.choice([n, n, n + 5, n - 1, 2 * n, n + 64, 0, 1]))
+        a, b = ref.decode(c, cap), port.decode(c, cap)
+        assert a[0] == b[0], (it, kind, n, cap)
+        if a[0] > 0 and b"\x00\x00" not in c:        # offset-0 content is unspecified
+            assert a[1] == b[1]
+        checked += 1
+    assert checked == 6000
+
+
+def test_enforce32_differs_only_for_large_inputs(port):
+    small = inputs.gen("text2", 65546, 3)
+    assert port.encode(small) == port.encode(small, enforce32=True)
+    big = inputs.gen("text2", 200000, 3)
+    a, b = port.encode(big), port.encode(big, enforce32=True)
+    assert port.decode(a[1], len(big))[1] == big and port.decode(b[1], len(big))[1] == big
+
+
+def test_config1_single_random_64k_block(port):
+    """BASELINE.json configs[0]: one 64 KiB random block, CPU, bit-exact roundtrip."""
+    data = np.random.default_rng(0).integers(0, 256, 65536, dtype=np.uint8).tobytes()
+    cap = port.max_output_size(65536)
+    assert cap == 65809
+    r, c = port.encode(data, cap)
+    assert 65536 < r <= cap
+    assert port.decode(c, 65536) == (65536, data)
+
+
+def test_codec_edge_semantics(port):
+    assert port.encode(b"", 10) == (0, b"")                 # LZ4Codec.cs:45-46
+    assert port.decode(b"", 10) == (0, b"")                 # LZ4Codec.cs:108-109
+    assert port.decode(b"\x00", 10)[0] == -1                # valid empty block decodes to 0 -> -1
+    assert port.decode(b"\x00", 0)[0] == -1
+    assert port.encode(b"abc", 1)[0] == -1                  # does not fit
+    assert port.encode(b"a" * 100, level=3)[0] == -2        # HC delegates
+    for n, v in [(0, 16), (1, 17), (255, 272), (65536, 65809), (0x7E000000, 0x7E000000 + 0x7E000000 // 255 + 16)]:
+        assert port.max_output_size(n) == v
+    assert port.max_output_size(0x7E000001) == 0
+
+
+def test_border_line_compression(port):
+    """BlockRoundtripTests.cs:114-125: encoding into exactly the required size succeeds."""
+    for kind in ("random", "text2", "lorem", "synth525"):
+        data = inputs.gen(kind, 65536, 11)
+        req, c = port.encode(data)
+        assert port.encode(data, req) == (req, c)
+        assert port.encode(data, req - 1)[0] == -1 or port.encode(data, req - 1)[0] == req
+
+
+def test_pickler_restatement(port):
+    """LZ4Pickler.pickle.cs:85-105,203-228 / unpickle.cs:131-158: header bytes by hand."""
+    assert port.pickle(b"") == b""
+    p = port.pickle(b"x")
+    assert p == b"\x00x"                                    # raw form
+    rnd = inputs.gen("random", 300, 1)
+    assert port.pickle(rnd) == b"\x00" + rnd                # incompressible -> raw
+    a = b"a" * 200
+    p = port.pickle(a)
+    enc = port.encode(a, 1024)[1]
+    assert p == bytes([0x40, 200 - len(enc)]) + enc         # diff <= 255 -> 1 byte
+    a = b"a" * 5000
+    p = port.pickle(a)
+    enc = port.encode(a, 5000)[1]
+    d = 5000 - len(enc)
+    assert p == bytes([0x80, d & 255, d >> 8]) + enc        # 2-byte diff
+    a = b"a" * 100000
+    p = port.pickle(a)
+    enc = port.encode(a, 100000)[1]
+    d = 100000 - len(enc)
+    assert p == bytes([0xC0]) + d.to_bytes(4, "little") + enc
+    for msg in (b"", b"x", rnd, b"a" * 200, b"a" * 5000, inputs.gen("text2", 1024, 2),
+                inputs.gen("text2", 1025, 2), inputs.gen("lorem", 4096, 0)):
+        p = port.pickle(msg)
+        if msg:
+            assert port.unpickled_size(p) == len(msg)
+        assert port.unpickle(p) == (len(msg), msg)
+    # corruption -> InvalidDataException (PicklingTests.cs:149-172)
+    import oracle
+    good = port.pickle(b"a" * 200)
+    assert port.unpickle(bytes([good[0] | 1]) + good[1:])[0] == oracle.PICKLE_CORRUPT   # version bits
+    assert port.unpickle(good[:-1])[0] == oracle.PICKLE_CORRUPT                           # truncated
+    assert port.unpickle(b"\xC0\x01")[0] == oracle.PICKLE_CORRUPT                         # short header
