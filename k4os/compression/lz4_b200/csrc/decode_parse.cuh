@@ -1,0 +1,179 @@
+// decode_parse.cuh -- pass 1 of the batched decoder: one THREAD per block walks the LZ4 token
+// chain (the only inherently serial part of decoding) and validates it exactly as the reference
+// does, emitting one 32-bit descriptor per sequence for the copy kernel.
+//
+// Why it looks the way it does (measured on B200, profiles/): a naive per-thread walk over global
+// memory runs at ~1 us per sequence -- 32 lanes stream 32 different blocks, nearly every step one
+// of them misses L1, and divergent branches serialise those latencies.  So
+//   * every lane owns a 256-byte ring in shared memory that it keeps filled with 16-byte
+//     cp.async copies issued ~8 steps ahead (one commit group per step, wait_group 8: data is
+//     consumed only after it has had 8 steps to land; a lane whose bytes are not there yet simply
+//     idles for that step instead of blocking the warp), and
+//   * the walk is a branch-light state machine executed in lock step by all lanes:
+//     TOKEN -> [LITVLE] -> LITEND -> OFFSET -> [MATCHVLE] -> MATCHCHK -> SEQEND -> TOKEN ...
+//     a lane runs through as many states per step as its ring has bytes for (normally a whole
+//     sequence).
+//
+// Semantics: LZ4_decompress_generic(endOnInputSize, full, noDict) --
+//   /root/reference/src/K4os.Compression.LZ4/Engine/x64/LL64.dec.cs:124-467; every accept/reject
+//   test is evaluated on the same values and in the same order, including the two-stage shortcut
+//   (:191-225) whose eligibility depends on the output position, and LZ4_readVLE's early stop
+//   (Engine/LL.tools.cs:165-193).  Results follow LZ4Codec.Decode (LZ4Codec.cs:104-115).
+#pragma once
+#include "common.cuh"
+
+namespace k4 {
+
+constexpr int TILE_BYTES = 65536;
+constexpr int DESC_CAP = 16640;          // >= 65536/4 + 2 descriptors per block, multiple of 128
+constexpr int MAX_BATCHES = (DESC_CAP + 31) / 32;   // 520
+constexpr int ST_OK = 1, ST_DONE = 0, ST_FALLBACK = 2;   // BlockInfo.status
+
+struct BlockInfo {
+    int32_t nseq;             // descriptors emitted
+    int32_t status;           // ST_OK: copy kernel materialises `outLen` bytes; ST_DONE: result already
+                              // final (empty / error); ST_FALLBACK: generic decoder takes the block
+    int32_t outLen;           // decoded size when ST_OK
+    int32_t lastIsTerminal;   // the last descriptor is the final literal-only sequence
+};
+
+constexpr int PARSE_THREADS = 128;
+constexpr int PR_RING = 256;             // bytes of ring per lane
+constexpr int PR_NCH = PR_RING / 16;     // 16-byte chunks per ring
+constexpr int PR_G = 8;                  // commit groups (= steps) a copy is given to land
+
+enum ParseState : int { PS_TOKEN = 0, PS_LITVLE, PS_LITEND, PS_OFFSET, PS_MATCHVLE, PS_MATCHCHK, PS_SEQEND,
+                        PS_FINAL_OK, PS_FINAL_ERR, PS_FINAL_FALLBACK };
+
+__global__ void __launch_bounds__(PARSE_THREADS)
+decode_parse_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restrict__ srcOff,
+                    const int32_t* __restrict__ srcLen, const int32_t* __restrict__ dstCap,
+                    int32_t* __restrict__ outLen, BlockInfo* __restrict__ info,
+                    uint32_t* __restrict__ descs, int first, int count) {
+    __shared__ __align__(16) uint8_t rings[PARSE_THREADS * PR_RING];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < count;
+    const int b = first + (live ? t : 0);
+    int n = live ? srcLen[b] : 0;
+    const int cap = live ? dstCap[b] : 0;
+    BlockInfo bi; bi.nseq = 0; bi.status = ST_DONE; bi.outLen = 0; bi.lastIsTerminal = 0;
+
+    int state = PS_TOKEN;
+    if (!live) state = PS_FINAL_ERR;
+    else if (n <= 0) { outLen[b] = 0; info[t] = bi; state = PS_FINAL_ERR; n = 0; }          // LZ4Codec.cs:108-109
+    else if (cap <= 0) { outLen[b] = -1; info[t] = bi; state = PS_FINAL_ERR; }              // LL64.dec.cs:162-168
+    const bool skipFinal = (state == PS_FINAL_ERR);      // result already written above
+
+    const uint8_t* src = srcBase + (live ? srcOff[b] : 0);
+    uint32_t* __restrict__ d = descs + (size_t)(live ? t : 0) * DESC_CAP;
+    const int shift = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+    const uint8_t* gbase = src - shift;                       // 16-byte aligned
+    const int nChunks = (n + shift + 15) >> 4;
+    uint8_t* ring = rings + threadIdx.x * PR_RING;
+    const uint32_t ringS = (uint32_t)__cvta_generic_to_shared(ring);
+
+    int ip = 0, op = 0;
+    const int iend = n, oend = cap;
+    const int shortiend = iend - 16, shortoend = oend - 32;                                  // :152-153
+    int req = 0;                      // next 16-byte chunk to request (absolute index from gbase)
+    int nseq = 0, result = -1;
+    int tokPos = 0, seqOut = 0, len = 0, match = 0;
+    uint32_t token = 0;
+    bool shortcut = false;
+
+#define PR_A(pos) ((pos) + shift)
+#define PR_RD(pos) ((uint32_t)ring[PR_A(pos) & (PR_RING - 1)])
+
+    while (__any_sync(FULL, state < PS_FINAL_OK)) {
+        // ---- keep the ring filled: at most one 16-byte copy per step per lane -------------------
+        const int curChunk = PR_A(ip) >> 4;
+        if (req < curChunk) req = curChunk;                   // jumped over a long literal run
+        if (state < PS_FINAL_OK && req < curChunk + PR_NCH) {
+            if (req < nChunks) {
+                const uint32_t sdst = ringS + (uint32_t)((req & (PR_NCH - 1)) << 4);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(sdst), "l"(gbase + ((size_t)req << 4)) : "memory");
+            }
+            req++;                                            // past the end the requests are virtual
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group %0;" :: "n"(PR_G) : "memory");
+        const int rdyEnd = (req - PR_G) << 4;                 // absolute byte bound of landed data
+#define PR_READY(pos, k) (PR_A(pos) + (k) <= rdyEnd)
+
+        // ---- the state machine (reference line numbers: LL64.dec.cs) ---------------------------------
+        if (state == PS_TOKEN && PR_READY(ip, 1)) {                                          // :177
+            tokPos = ip;
+            token = PR_RD(ip); ip++;
+            len = (int)(token >> 4);
+            shortcut = (len != 15) && (ip < shortiend) && (op <= shortoend);                // :191-193
+            if (len == 15) state = (ip >= iend - 15) ? PS_FINAL_ERR : PS_LITVLE;            // :231-232
+            else state = PS_LITEND;
+        }
+        if (state == PS_LITVLE) {                                                            // LL.tools.cs:165-193
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                if (state == PS_LITVLE && PR_READY(ip, 1)) {
+                    const uint32_t s = PR_RD(ip); ip++;
+                    len += (int)s;
+                    if (ip >= iend - 15 || s != 255) state = PS_LITEND;   // loop_error only stops the sum
+                }
+            }
+        }
+        if (state == PS_LITEND) {
+            if (!shortcut) {
+                const int cpy = op + len;                                                    // :246
+                if (cpy > oend - MFLIMIT || ip + len > iend - (2 + 1 + LASTLITERALS)) {
+                    if (ip + len != iend || cpy > oend) state = PS_FINAL_ERR;                // :291-294
+                    else if (cpy > TILE_BYTES || tokPos > 65535 || (len > 0 && op > 65535)) state = PS_FINAL_FALLBACK;
+                    else {
+                        if (len > 0) { d[nseq++] = (uint32_t)tokPos | ((uint32_t)op << 16); bi.lastIsTerminal = 1; }
+                        result = cpy;                                                        // :454-457
+                        state = PS_FINAL_OK;
+                    }
+                }
+            }
+            if (state == PS_LITEND) { seqOut = op; ip += len; op += len; state = PS_OFFSET; }
+        }
+        if (state == PS_OFFSET && PR_READY(ip, 2)) {                                         // :205 / :318
+            const int offset = (int)(PR_RD(ip) | (PR_RD(ip + 1) << 8));
+            ip += 2;
+            match = op - offset;
+            len = (int)(token & 15);
+            if (shortcut && len != 15 && offset >= 8 && match >= 0) state = PS_SEQEND;       // :211-220
+            else state = (len == 15) ? PS_MATCHVLE : PS_MATCHCHK;
+        }
+        if (state == PS_MATCHVLE) {                                                          // :326-334
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                if (state == PS_MATCHVLE && PR_READY(ip, 1)) {
+                    const uint32_t s = PR_RD(ip); ip++;
+                    len += (int)s;
+                    if (ip >= iend - LASTLITERALS + 1) state = PS_FINAL_ERR;
+                    else if (s != 255) state = PS_MATCHCHK;
+                }
+            }
+        }
+        if (state == PS_MATCHCHK) {
+            if (match < 0 || op + len + MINMATCH > oend - LASTLITERALS) state = PS_FINAL_ERR;   // :338, :427-433
+            else state = PS_SEQEND;
+        }
+        if (state == PS_SEQEND) {
+            op += len + MINMATCH;
+            if (op > TILE_BYTES || tokPos > 65535 || seqOut > 65535) state = PS_FINAL_FALLBACK;
+            else { d[nseq++] = (uint32_t)tokPos | ((uint32_t)seqOut << 16); state = PS_TOKEN; }
+        }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#undef PR_A
+#undef PR_RD
+#undef PR_READY
+
+    if (!live || skipFinal) return;
+    if (state == PS_FINAL_FALLBACK) { bi.status = ST_FALLBACK; info[t] = bi; return; }       // outLen by the fallback
+    if (state != PS_FINAL_OK || result <= 0) { outLen[b] = -1; info[t] = bi; return; }       // LZ4Codec.cs:114
+    outLen[b] = result;
+    bi.nseq = nseq; bi.status = ST_OK; bi.outLen = result;
+    info[t] = bi;
+}
+
+}  // namespace k4

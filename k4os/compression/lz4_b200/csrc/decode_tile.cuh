@@ -1,21 +1,411 @@
-// decode_tile.cuh -- launch policy of the batched decoder.
-// v0: every block goes through the warp-per-block global-memory decoder (decode_generic.cuh).
+// decode_tile.cuh -- pass 2 of the batched LZ4 block decoder for B200, and the launch policy.
+//
+//   pass 1  decode_parse.cuh   thread per block: validated sequence descriptors
+//   pass 2  decode_copy_kernel one CTA per block.  The compressed block is pulled into shared
+//           memory with TMA bulk copies (cp.async.bulk global -> shared, 8 KiB pieces, one
+//           mbarrier each) and the 64 KiB output tile is built in shared memory as well, so
+//           every byte the copy loop touches is a shared-memory access.  Warps take batches of
+//           32 consecutive sequences, ONE SEQUENCE PER LANE: lane-parallel literal copies, then
+//           lane-parallel match copies once the batches that produce their source bytes are
+//           flagged done (per-batch done flags + a 128-byte-granule -> batch map give exact
+//           batch-level dependencies, so independent batches never wait for each other).  Long
+//           runs are copied by the whole warp.  The finished tile leaves through one TMA bulk
+//           store (cp.async.bulk shared -> global).
+//
+// Two instantiations: STAGE = 47 KiB (two CTAs per SM; blocks whose compressed size fits) and
+// STAGE = 66 KiB (one CTA per SM; everything else that still fits the 64 KiB tile).  Blocks that
+// do not fit the tile at all (decoded size > 64 KiB) go to the warp-per-block generic decoder.
+//
+// Reference semantics: /root/reference/src/K4os.Compression.LZ4/Engine/x64/LL64.dec.cs:124-477,
+// Engine/LL.tools.cs:165-193 (LZ4_readVLE), LZ4Codec.cs:104-115.
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 #include "decode_generic.cuh"
+#include "decode_parse.cuh"
 
 namespace k4 {
 
+constexpr int SUB_BATCH = 65536;         // blocks per parse/copy kernel pair
+#ifndef K4_COPY_THREADS
+#define K4_COPY_THREADS 512
+#endif
+constexpr int COPY_THREADS = K4_COPY_THREADS;
+constexpr int COPY_WARPS = COPY_THREADS / 32;
+constexpr int GRAN_SHIFT = 5;            // 32-byte granules of the output tile
+constexpr int N_GRAN = TILE_BYTES >> GRAN_SHIFT;    // 2048
+constexpr int STAGE_PIECE = 8192;        // bytes per TMA bulk load / mbarrier
+constexpr int STAGE_SMALL = 42 * 1024;   // compressed bytes (incl. alignment slack) staged, 2 CTAs/SM
+constexpr int STAGE_BIG = 66 * 1024;     // ... 1 CTA/SM; covers LZ4_compressBound(65536) + slack
+constexpr int MAX_PIECES = (STAGE_BIG + STAGE_PIECE - 1) / STAGE_PIECE;   // 9
+
+template <int STAGE>
+struct CopySmem {
+    uint8_t tile[TILE_BYTES];
+    uint8_t stage[STAGE];
+    uint16_t gran[N_GRAN + 2];                 // granule -> sequence holding the granule's first byte
+    volatile uint32_t done[MAX_BATCHES + 8];   // bit k%32 of word k/32: sequence k is final in the tile
+    unsigned long long bar[MAX_PIECES];        // one mbarrier per staged piece
+};
+
+__device__ __forceinline__ void tma_store_tile(uint8_t* gdst, const uint8_t* stile, int bytes) {
+    // generic-proxy writes -> async proxy, then one bulk copy shared::cta -> global
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(stile);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+// WAITMODE: 0 = spin, 1 = spin with nanosleep back-off, 2 = no waiting (timing experiments only)
+template <int STAGE, int WAITMODE>
+__global__ void __launch_bounds__(COPY_THREADS, (COPY_THREADS <= 512 ? 2 : 1))
+decode_copy_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restrict__ srcOff,
+                   const int32_t* __restrict__ srcLen, uint8_t* __restrict__ dstBase,
+                   const int64_t* __restrict__ dstOff, const int32_t* __restrict__ dstCap,
+                   int32_t* __restrict__ outLen, const BlockInfo* __restrict__ info,
+                   const uint32_t* __restrict__ descs, int first) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    CopySmem<STAGE>& S = *reinterpret_cast<CopySmem<STAGE>*>(smem_raw);
+    const int t = blockIdx.x;
+    const int b = first + t;
+    const BlockInfo bi = info[t];
+    const int lane = threadIdx.x & 31;
+    // the hardware arbiter favours high warp ids: give them the EARLIEST batches, the ones every
+    // other warp may be waiting for
+    const int warp = COPY_WARPS - 1 - (int)(threadIdx.x >> 5);
+
+    if (bi.status == ST_DONE) return;
+    const uint8_t* __restrict__ src = srcBase + srcOff[b];
+    const int n = srcLen[b];
+    const int shift = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+    const int staged = (n + shift + 15) & ~15;           // bytes pulled in, from the aligned base
+    const bool big = staged > STAGE_SMALL;
+    if (bi.status == ST_FALLBACK || staged > STAGE_BIG) {
+        if (STAGE != STAGE_SMALL) return;                // handled once, by the small-stage launch
+        if (warp == 0) {
+            const int r = codec_decode_warp(src, n, dstBase + dstOff[b], dstCap[b]);
+            if (lane == 0) outLen[b] = r;
+        }
+        return;
+    }
+    if (big != (STAGE == STAGE_BIG)) return;             // the other instantiation owns this block
+
+    const uint32_t* __restrict__ d = descs + (size_t)t * DESC_CAP;
+    const int nseq = bi.nseq;
+    const int nbatch = (nseq + 31) >> 5;
+    uint8_t* tile = S.tile;
+    const uint8_t* stg = S.stage + shift;                // stg[p] == src[p]
+    const int npieces = (staged + STAGE_PIECE - 1) / STAGE_PIECE;
+
+    // ---- prologue: TMA loads of the compressed block, done flags, granule -> batch map ---------
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < npieces; i++) {
+            const uint32_t a = (uint32_t)__cvta_generic_to_shared(&S.bar[i]);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(a) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint8_t* gsrc = src - shift;
+        for (int i = 0; i < npieces; i++) {
+            const int off = i * STAGE_PIECE;
+            const int bytes = (staged - off) < STAGE_PIECE ? (staged - off) : STAGE_PIECE;
+            const uint32_t a = (uint32_t)__cvta_generic_to_shared(&S.bar[i]);
+            const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(S.stage + off);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(a), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(sdst), "l"(gsrc + off), "r"(bytes), "r"(a) : "memory");
+        }
+    }
+    for (int i = threadIdx.x; i < nbatch; i += COPY_THREADS) S.done[i] = 0;
+    for (int k = threadIdx.x; k < nseq; k += COPY_THREADS) {
+        // granules whose first byte lies inside sequence k's output range map to k
+        const int o0 = (int)(__ldg(d + k) >> 16);
+        const int o1 = (k + 1 < nseq) ? (int)(__ldg(d + k + 1) >> 16) : TILE_BYTES;
+        const int g0 = (o0 + (1 << GRAN_SHIFT) - 1) >> GRAN_SHIFT;
+        const int g1 = (k + 1 < nseq) ? ((o1 + (1 << GRAN_SHIFT) - 1) >> GRAN_SHIFT) : N_GRAN;
+        for (int g = g0; g < g1; g++) S.gran[g] = (uint16_t)k;
+    }
+    if (threadIdx.x == 0) { S.gran[N_GRAN] = (uint16_t)(nseq - 1); S.gran[N_GRAN + 1] = (uint16_t)(nseq - 1); }
+    __syncthreads();
+
+    // ---- batches: one sequence per lane -----------------------------------------------------------
+    int piecesSeen = 0;                                   // staged pieces this warp has waited for
+    uint32_t descNext = (warp < nbatch && warp * 32 + lane < nseq) ? __ldg(d + warp * 32 + lane) : 0u;
+    for (int bt = warp; bt < nbatch; bt += COPY_WARPS) {
+        const int k = bt * 32 + lane;
+        const bool valid = k < nseq;
+        const uint32_t desc = descNext;
+        {   // prefetch this warp's next descriptors
+            const int kn = k + COPY_WARPS * 32;
+            descNext = (kn < nseq) ? __ldg(d + kn) : 0u;
+        }
+        const uint32_t tokPos = desc & 0xFFFFu;
+        const int dst = (int)(desc >> 16);
+        const int batchOut = __shfl_sync(FULL, dst, 0);
+        // the staged pieces holding this batch's sequence headers (a header = token + length bytes,
+        // at most ~260 bytes for a 64 KiB block); literal extents are waited for below
+        {
+            const int lastTok = __reduce_max_sync(FULL, valid ? (int)tokPos : 0);
+            int needPieces = (lastTok + 600 + shift + STAGE_PIECE - 1) / STAGE_PIECE;
+            if (needPieces > npieces) needPieces = npieces;
+            while (piecesSeen < needPieces) { mbar_wait(&S.bar[piecesSeen], 0); piecesSeen++; }
+        }
+
+        // sequence header (lengths already validated by the parse kernel)
+        int lit = 0, ml = 0, offset = 0;
+        uint32_t litSrc = 0;
+        bool hasMatch = false;
+        if (valid) {
+            const uint32_t token = stg[tokPos];
+            uint32_t p = tokPos + 1;
+            lit = (int)(token >> 4);
+            if (lit == 15) {                                   // LZ4_readVLE incl. its early stop
+                for (;;) {
+                    const uint32_t s = stg[p]; p++;
+                    lit += (int)s;
+                    if ((int)p >= n - 15) break;
+                    if (s != 255) break;
+                }
+            }
+            litSrc = p;
+            hasMatch = !(bi.lastIsTerminal && k == nseq - 1);
+        }
+        {   // every staged byte this batch reads (literals, then offset + match length bytes)
+            const int endMax = __reduce_max_sync(FULL, valid ? (int)litSrc + lit + 300 : 0);
+            int needPieces = (endMax + shift + STAGE_PIECE - 1) / STAGE_PIECE;
+            if (needPieces > npieces) needPieces = npieces;
+            while (piecesSeen < needPieces) { mbar_wait(&S.bar[piecesSeen], 0); piecesSeen++; }
+        }
+        if (hasMatch) {
+            uint32_t p = litSrc + (uint32_t)lit;
+            offset = (int)stg[p] | ((int)stg[p + 1] << 8);
+            p += 2;
+            ml = (int)(stg[tokPos] & 15);
+            if (ml == 15) {
+                for (;;) { const uint32_t s = stg[p]; p++; ml += (int)s; if (s != 255) break; }
+            }
+            ml += MINMATCH;
+        }
+        // literals: short runs lane-parallel (all loads, then all stores), long runs by the whole warp
+        {
+            const int shortLit = lit < 15 ? lit : 0;
+            const int mx = __reduce_max_sync(FULL, shortLit);
+            if (mx > 0) {
+                uint8_t v[14];
+                if (mx <= 7) {
+#pragma unroll
+                    for (int j = 0; j < 7; j++) if (j < shortLit) v[j] = stg[litSrc + j];
+#pragma unroll
+                    for (int j = 0; j < 7; j++) if (j < shortLit) tile[dst + j] = v[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 14; j++) if (j < shortLit) v[j] = stg[litSrc + j];
+#pragma unroll
+                    for (int j = 0; j < 14; j++) if (j < shortLit) tile[dst + j] = v[j];
+                }
+            }
+            unsigned longMask = __ballot_sync(FULL, lit >= 15);
+            while (longMask) {
+                const int l = __ffs(longMask) - 1;
+                longMask &= longMask - 1;
+                const uint32_t s0 = __shfl_sync(FULL, litSrc, l);
+                const int d0 = __shfl_sync(FULL, dst, l);
+                const int len = __shfl_sync(FULL, lit, l);
+                for (int i = lane; i < len; i += 32) tile[d0 + i] = stg[s0 + i];
+            }
+        }
+
+        // match geometry + dependencies
+        const int mdst = dst + lit;
+        const int msrc = mdst - offset;
+        // bytes of the source that OTHER sequences produce: [msrc, srcEndOther); the rest (if any)
+        // are this lane's own literals / own earlier match bytes (overlapping copy)
+        const int srcEndOther = (msrc + ml < dst) ? msrc + ml : dst;
+        const bool reads = hasMatch && offset > 0 && msrc < dst;
+        // sequences whose output the match reads: a conservative index range [lo, hi] from the
+        // 32-byte granule map (a sequence is flagged only when all its bytes are final)
+        int lo = 1, hi = 0;
+        if (reads) {
+            lo = S.gran[msrc >> GRAN_SHIFT];
+            hi = S.gran[((srcEndOther - 1) >> GRAN_SHIFT) + 1];
+            if (hi > k - 1) hi = k - 1;
+        }
+        auto deps_done = [&]() {
+            bool r = true;
+            if (WAITMODE != 2 && lo <= hi) {
+                const int w0 = lo >> 5, w1 = hi >> 5;
+                for (int w = w0; w <= w1; w++) {
+                    uint32_t need = 0xffffffffu;
+                    if (w == w0) need &= 0xffffffffu << (lo & 31);
+                    if (w == w1) need &= 0xffffffffu >> (31 - (hi & 31));
+                    r = r && ((S.done[w] & need) == need);
+                }
+            }
+            return r;
+        };
+        auto copy_matches = [&](const bool sel) {
+            // (1) short non-overlapping matches: all loads first, then all stores
+            {
+                const int m1 = (sel && ml <= 18 && offset >= ml) ? ml : 0;
+                const int mx = __reduce_max_sync(FULL, m1);
+                if (mx > 0) {
+                    uint8_t v[18];
+                    if (mx <= 8) {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) if (j < m1) v[j] = tile[msrc + j];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) if (j < m1) tile[mdst + j] = v[j];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 18; j++) if (j < m1) v[j] = tile[msrc + j];
+#pragma unroll
+                        for (int j = 0; j < 18; j++) if (j < m1) tile[mdst + j] = v[j];
+                    }
+                }
+            }
+            // (2) short overlapping matches (offset < ml, or offset 0): in-order byte loop per lane
+            {
+                const int m2 = (sel && ml <= 18 && offset < ml) ? ml : 0;
+                const int mx = __reduce_max_sync(FULL, m2);
+                if (offset > 0) { for (int j = 0; j < mx; j++) if (j < m2) tile[mdst + j] = tile[msrc + j]; }
+                else            { for (int j = 0; j < mx; j++) if (j < m2) tile[mdst + j] = 0; }
+            }
+            // (3) long matches, whole warp each
+            unsigned longMask = __ballot_sync(FULL, sel && ml > 18);
+            while (longMask) {
+                const int l = __ffs(longMask) - 1;
+                longMask &= longMask - 1;
+                const int s0 = __shfl_sync(FULL, msrc, l);
+                const int d0 = __shfl_sync(FULL, mdst, l);
+                const int len = __shfl_sync(FULL, ml, l);
+                const int off = d0 - s0;
+                if (off == 0)          for (int i = lane; i < len; i += 32) tile[d0 + i] = 0;
+                else if (off >= len)   for (int i = lane; i < len; i += 32) tile[d0 + i] = tile[s0 + i];
+                else                   for (int i = lane; i < len; i += 32) tile[d0 + i] = tile[s0 + (i % off)];
+            }
+        };
+
+        // rounds: copy every match whose source sequences are final, publish, repeat.  Sequences
+        // only ever wait for lower-numbered ones, so the lowest unfinished sequence can always go.
+        __threadfence_block();
+        __syncwarp();                       // this batch's literal stores are visible to all lanes
+        bool pending = hasMatch;
+        unsigned publish = __ballot_sync(FULL, !hasMatch);      // literal-only / padding lanes are final now
+        for (;;) {
+            const bool go = pending && deps_done();
+            const unsigned goMask = __ballot_sync(FULL, go);
+            if (goMask) {
+                __threadfence_block();      // acquire: the flagged sequences' bytes
+                copy_matches(go);
+                pending = pending && !go;
+                publish |= goMask;
+            }
+            if (publish) {
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) atomicOr(const_cast<uint32_t*>(&S.done[bt]), publish);
+                publish = 0;
+            }
+            if (!__any_sync(FULL, pending)) break;
+            if (!goMask && WAITMODE == 1) __nanosleep(20);      // nothing was ready: back off
+        }
+    }
+
+    __syncthreads();
+
+    // ---- tile -> global ------------------------------------------------------------------------------
+    uint8_t* gdst = dstBase + dstOff[b];
+    const int total = bi.outLen;
+    if ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0) {
+        const int bulk = total & ~15;
+        if (threadIdx.x == 0 && bulk > 0) tma_store_tile(gdst, tile, bulk);
+        for (int i = bulk + threadIdx.x; i < total; i += COPY_THREADS) gdst[i] = tile[i];
+    } else {
+        // unaligned destination: byte head up to 4-byte alignment, then words built from the tile
+        const int head = (int)((4 - (reinterpret_cast<uintptr_t>(gdst) & 3)) & 3);
+        const int h = head < total ? head : total;
+        for (int i = threadIdx.x; i < h; i += COPY_THREADS) gdst[i] = tile[i];
+        const int words = (total - h) >> 2;
+        uint32_t* g4 = reinterpret_cast<uint32_t*>(gdst + h);
+        for (int i = threadIdx.x; i < words; i += COPY_THREADS) {
+            const uint8_t* s = tile + h + 4 * i;
+            g4[i] = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24);
+        }
+        for (int i = h + 4 * words + threadIdx.x; i < total; i += COPY_THREADS) gdst[i] = tile[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launcher
+// ------------------------------------------------------------------------------------------------
+template <int STAGE, int W>
+inline void decode_copy_launch_t(const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen,
+                                 uint8_t* dstBase, const int64_t* dstOff, const int32_t* dstCap,
+                                 int32_t* outLen, const BlockInfo* info, const uint32_t* descs,
+                                 int first, int count, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(decode_copy_kernel<STAGE, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(CopySmem<STAGE>));
+        attr = true;
+    }
+    decode_copy_kernel<STAGE, W><<<count, COPY_THREADS, sizeof(CopySmem<STAGE>), st>>>(
+        srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, info, descs, first);
+}
+
 inline void decode_tile_set_attrs() {}
 
-// returns the number of kernels launched
+// returns the number of kernels launched, or -1 on a CUDA error (cudaGetLastError has it)
 inline int decode_tile_launch(const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen,
                               uint8_t* dstBase, const int64_t* dstOff, const int32_t* dstCap,
                               int32_t* outLen, int n, cudaStream_t st) {
-    const int ctas = (n + 3) / 4;
-    decode_generic_kernel<<<ctas, 128, 0, st>>>(srcBase, srcOff, srcLen, dstBase, dstOff, dstCap,
-                                                outLen, n, nullptr, n);
-    return 1;
+    static const int variant = [] { const char* e = getenv("K4LZ4_COPY_VARIANT"); return e ? atoi(e) : 0; }();
+    static const int subEnv = [] { const char* e = getenv("K4LZ4_SUB_BATCH"); return e ? atoi(e) : SUB_BATCH; }();
+    const int sub = n < subEnv ? n : subEnv;
+    {   // keep the stream-ordered pool's memory across calls (default: released at every sync)
+        static bool poolSet[64] = {false};
+        int dev = 0; cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !poolSet[dev]) {
+            cudaMemPool_t pool; 
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long thr = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
+            poolSet[dev] = true;
+        }
+    }
+    uint32_t* descs = nullptr;
+    BlockInfo* info = nullptr;
+    if (cudaMallocAsync(&descs, (size_t)sub * DESC_CAP * sizeof(uint32_t), st) != cudaSuccess) return -1;
+    if (cudaMallocAsync(&info, (size_t)sub * sizeof(BlockInfo), st) != cudaSuccess) { cudaFreeAsync(descs, st); return -1; }
+    int launches = 0;
+    for (int first = 0; first < n; first += sub) {
+        const int count = (n - first) < sub ? (n - first) : sub;
+        decode_parse_kernel<<<(count + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(
+            srcBase, srcOff, srcLen, dstCap, outLen, info, descs, first, count);
+        launches++;
+#define K4_COPY(STG, W) decode_copy_launch_t<STG, W>(srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, info, descs, first, count, st)
+        switch (variant) {
+        case 1: K4_COPY(STAGE_SMALL, 0); K4_COPY(STAGE_BIG, 0); launches += 2; break;
+        case 2: K4_COPY(STAGE_SMALL, 2); K4_COPY(STAGE_BIG, 2); launches += 2; break;
+        case 9: break;                                     // parse only (timing experiments)
+        default: K4_COPY(STAGE_SMALL, 1); K4_COPY(STAGE_BIG, 1); launches += 2; break;
+        }
+#undef K4_COPY
+    }
+    cudaFreeAsync(descs, st);
+    cudaFreeAsync(info, st);
+    return launches;
 }
 
 }  // namespace k4

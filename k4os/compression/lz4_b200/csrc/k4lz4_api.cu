@@ -97,10 +97,13 @@ cudaError_t launch_op(Op op, const DevArgs& a, cudaStream_t st) {
         g_launches++;
         break;
     }
-    case OP_DECODE:
-        g_launches += k4::decode_tile_launch(a.srcBase, a.srcOff, a.srcLen, a.dstBase, a.dstOff,
-                                             a.dstCap, a.outLen, a.n, st);
+    case OP_DECODE: {
+        const int nl = k4::decode_tile_launch(a.srcBase, a.srcOff, a.srcLen, a.dstBase, a.dstOff,
+                                              a.dstCap, a.outLen, a.n, st);
+        if (nl < 0) { cudaError_t e = cudaGetLastError(); return e != cudaSuccess ? e : cudaErrorMemoryAllocation; }
+        g_launches += nl;
         break;
+    }
     case OP_PICKLE: {
         const int ctas = (a.n + k4::ENC_WARPS_PER_CTA - 1) / k4::ENC_WARPS_PER_CTA;
         k4::pickle_kernel<<<ctas, k4::ENC_WARPS_PER_CTA * 32,
