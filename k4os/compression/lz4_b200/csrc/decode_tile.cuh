@@ -35,7 +35,7 @@ constexpr int COPY_WARPS = COPY_THREADS / 32;
 constexpr int GRAN_SHIFT = 5;            // 32-byte granules of the output tile
 constexpr int N_GRAN = TILE_BYTES >> GRAN_SHIFT;    // 2048
 constexpr int STAGE_PIECE = 8192;        // bytes per TMA bulk load / mbarrier
-constexpr int STAGE_SMALL = 42 * 1024;   // compressed bytes (incl. alignment slack) staged, 2 CTAs/SM
+constexpr int STAGE_SMALL = 40 * 1024;   // compressed bytes (incl. alignment slack) staged, 2 CTAs/SM
 constexpr int STAGE_BIG = 66 * 1024;     // ... 1 CTA/SM; covers LZ4_compressBound(65536) + slack
 constexpr int MAX_PIECES = (STAGE_BIG + STAGE_PIECE - 1) / STAGE_PIECE;   // 9
 
@@ -43,8 +43,7 @@ template <int STAGE>
 struct CopySmem {
     uint8_t tile[TILE_BYTES];
     uint8_t stage[STAGE];
-    uint16_t gran[N_GRAN + 2];                 // granule -> sequence holding the granule's first byte
-    volatile uint32_t done[MAX_BATCHES + 8];   // bit k%32 of word k/32: sequence k is final in the tile
+    volatile uint32_t ready[TILE_BYTES / 32];  // one bit per output byte: the byte is final in the tile
     unsigned long long bar[MAX_PIECES];        // one mbarrier per staged piece
 };
 
@@ -126,16 +125,7 @@ decode_copy_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restric
                          :: "r"(sdst), "l"(gsrc + off), "r"(bytes), "r"(a) : "memory");
         }
     }
-    for (int i = threadIdx.x; i < nbatch; i += COPY_THREADS) S.done[i] = 0;
-    for (int k = threadIdx.x; k < nseq; k += COPY_THREADS) {
-        // granules whose first byte lies inside sequence k's output range map to k
-        const int o0 = (int)(__ldg(d + k) >> 16);
-        const int o1 = (k + 1 < nseq) ? (int)(__ldg(d + k + 1) >> 16) : TILE_BYTES;
-        const int g0 = (o0 + (1 << GRAN_SHIFT) - 1) >> GRAN_SHIFT;
-        const int g1 = (k + 1 < nseq) ? ((o1 + (1 << GRAN_SHIFT) - 1) >> GRAN_SHIFT) : N_GRAN;
-        for (int g = g0; g < g1; g++) S.gran[g] = (uint16_t)k;
-    }
-    if (threadIdx.x == 0) { S.gran[N_GRAN] = (uint16_t)(nseq - 1); S.gran[N_GRAN + 1] = (uint16_t)(nseq - 1); }
+    for (int i = threadIdx.x; i < TILE_BYTES / 32; i += COPY_THREADS) S.ready[i] = 0;
     __syncthreads();
 
     // ---- batches: one sequence per lane -----------------------------------------------------------
@@ -196,7 +186,48 @@ decode_copy_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restric
             }
             ml += MINMATCH;
         }
-        // literals: short runs lane-parallel (all loads, then all stores), long runs by the whole warp
+        // helpers on the byte-readiness bitmap -----------------------------------------------------
+        // mark [a, a+len) final (len <= 32: at most two words)
+        auto publish_short = [&](const int a, const int len) {
+            if (len > 0) {
+                const unsigned long long m = ((len >= 64 ? 0ull : (1ull << len)) - 1ull) << (a & 31);
+                uint32_t* w = const_cast<uint32_t*>(&S.ready[a >> 5]);
+                atomicOr(w, (uint32_t)m);
+                if ((uint32_t)(m >> 32)) atomicOr(w + 1, (uint32_t)(m >> 32));
+            }
+        };
+        // are all bytes of [a, a+len) final? (len <= 32)
+        auto ready_short = [&](const int a, const int len) -> bool {
+            if (len <= 0) return true;
+            const unsigned long long m = ((1ull << len) - 1ull) << (a & 31);
+            const uint32_t lo32 = (uint32_t)m, hi32 = (uint32_t)(m >> 32);
+            bool r = (S.ready[a >> 5] & lo32) == lo32;
+            if (hi32) r = r && ((S.ready[(a >> 5) + 1] & hi32) == hi32);
+            return r;
+        };
+        // whole-warp versions for runs of any length (uniform arguments)
+        auto publish_long = [&](const int a, const int len) {
+            const int w0 = a >> 5, w1 = (a + len - 1) >> 5;
+            for (int w = w0 + lane; w <= w1; w += 32) {
+                const int b0 = (w << 5) > a ? (w << 5) : a;
+                const int b1 = ((w + 1) << 5) < (a + len) ? ((w + 1) << 5) : (a + len);
+                const uint32_t m = (uint32_t)(((1ull << (b1 - b0)) - 1ull) << (b0 & 31));
+                atomicOr(const_cast<uint32_t*>(&S.ready[w]), m);
+            }
+        };
+        auto ready_long = [&](const int a, const int len) -> bool {
+            const int w0 = a >> 5, w1 = (a + len - 1) >> 5;
+            bool r = true;
+            for (int w = w0 + lane; w <= w1; w += 32) {
+                const int b0 = (w << 5) > a ? (w << 5) : a;
+                const int b1 = ((w + 1) << 5) < (a + len) ? ((w + 1) << 5) : (a + len);
+                const uint32_t m = (uint32_t)(((1ull << (b1 - b0)) - 1ull) << (b0 & 31));
+                r = r && ((S.ready[w] & m) == m);
+            }
+            return __all_sync(FULL, r);
+        };
+
+        // ---- literals: short runs lane-parallel (all loads, then all stores), long runs by the warp -----
         {
             const int shortLit = lit < 15 ? lit : 0;
             const int mx = __reduce_max_sync(FULL, shortLit);
@@ -213,6 +244,8 @@ decode_copy_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restric
 #pragma unroll
                     for (int j = 0; j < 14; j++) if (j < shortLit) tile[dst + j] = v[j];
                 }
+                __threadfence_block();
+                publish_short(dst, shortLit);
             }
             unsigned longMask = __ballot_sync(FULL, lit >= 15);
             while (longMask) {
@@ -222,105 +255,79 @@ decode_copy_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restric
                 const int d0 = __shfl_sync(FULL, dst, l);
                 const int len = __shfl_sync(FULL, lit, l);
                 for (int i = lane; i < len; i += 32) tile[d0 + i] = stg[s0 + i];
+                __threadfence_block();
+                __syncwarp();
+                publish_long(d0, len);
             }
         }
 
-        // match geometry + dependencies
+        // ---- matches: exact byte-level dependencies ---------------------------------------------------
         const int mdst = dst + lit;
         const int msrc = mdst - offset;
-        // bytes of the source that OTHER sequences produce: [msrc, srcEndOther); the rest (if any)
-        // are this lane's own literals / own earlier match bytes (overlapping copy)
-        const int srcEndOther = (msrc + ml < dst) ? msrc + ml : dst;
-        const bool reads = hasMatch && offset > 0 && msrc < dst;
-        // sequences whose output the match reads: a conservative index range [lo, hi] from the
-        // 32-byte granule map (a sequence is flagged only when all its bytes are final)
-        int lo = 1, hi = 0;
-        if (reads) {
-            lo = S.gran[msrc >> GRAN_SHIFT];
-            hi = S.gran[((srcEndOther - 1) >> GRAN_SHIFT) + 1];
-            if (hi > k - 1) hi = k - 1;
-        }
-        auto deps_done = [&]() {
-            bool r = true;
-            if (WAITMODE != 2 && lo <= hi) {
-                const int w0 = lo >> 5, w1 = hi >> 5;
-                for (int w = w0; w <= w1; w++) {
-                    uint32_t need = 0xffffffffu;
-                    if (w == w0) need &= 0xffffffffu << (lo & 31);
-                    if (w == w1) need &= 0xffffffffu >> (31 - (hi & 31));
-                    r = r && ((S.done[w] & need) == need);
-                }
-            }
-            return r;
-        };
-        auto copy_matches = [&](const bool sel) {
-            // (1) short non-overlapping matches: all loads first, then all stores
-            {
-                const int m1 = (sel && ml <= 18 && offset >= ml) ? ml : 0;
-                const int mx = __reduce_max_sync(FULL, m1);
-                if (mx > 0) {
-                    uint8_t v[18];
-                    if (mx <= 8) {
+        // bytes actually read: an overlapping match (offset < ml) only reads [msrc, mdst)
+        const int srcLen = hasMatch ? (offset == 0 ? 0 : (offset < ml ? offset : ml)) : 0;
+        bool pendS = hasMatch && ml <= 18;                 // short: lane-parallel
+        unsigned pendL = __ballot_sync(FULL, hasMatch && ml > 18);   // long: whole warp, one at a time
+        for (;;) {
+            bool progress = false;
+            // short matches whose source bytes are all final
+            const bool go = pendS && (WAITMODE == 2 || ready_short(msrc, srcLen));
+            if (__any_sync(FULL, go)) {
+                __threadfence_block();                     // acquire the flagged bytes
+                {   // non-overlapping: all loads first, then all stores
+                    const int m1 = (go && offset >= ml) ? ml : 0;
+                    const int mx = __reduce_max_sync(FULL, m1);
+                    if (mx > 0) {
+                        uint8_t v[18];
+                        if (mx <= 8) {
 #pragma unroll
-                        for (int j = 0; j < 8; j++) if (j < m1) v[j] = tile[msrc + j];
+                            for (int j = 0; j < 8; j++) if (j < m1) v[j] = tile[msrc + j];
 #pragma unroll
-                        for (int j = 0; j < 8; j++) if (j < m1) tile[mdst + j] = v[j];
-                    } else {
+                            for (int j = 0; j < 8; j++) if (j < m1) tile[mdst + j] = v[j];
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 18; j++) if (j < m1) v[j] = tile[msrc + j];
+                            for (int j = 0; j < 18; j++) if (j < m1) v[j] = tile[msrc + j];
 #pragma unroll
-                        for (int j = 0; j < 18; j++) if (j < m1) tile[mdst + j] = v[j];
+                            for (int j = 0; j < 18; j++) if (j < m1) tile[mdst + j] = v[j];
+                        }
                     }
                 }
+                {   // overlapping (offset < ml) or offset 0: in-order byte loop per lane
+                    const int m2 = (go && offset < ml) ? ml : 0;
+                    const int mx = __reduce_max_sync(FULL, m2);
+                    if (offset > 0) { for (int j = 0; j < mx; j++) if (j < m2) tile[mdst + j] = tile[msrc + j]; }
+                    else            { for (int j = 0; j < mx; j++) if (j < m2) tile[mdst + j] = 0; }
+                }
+                __threadfence_block();
+                if (go) publish_short(mdst, ml);
+                pendS = pendS && !go;
+                progress = true;
             }
-            // (2) short overlapping matches (offset < ml, or offset 0): in-order byte loop per lane
-            {
-                const int m2 = (sel && ml <= 18 && offset < ml) ? ml : 0;
-                const int mx = __reduce_max_sync(FULL, m2);
-                if (offset > 0) { for (int j = 0; j < mx; j++) if (j < m2) tile[mdst + j] = tile[msrc + j]; }
-                else            { for (int j = 0; j < mx; j++) if (j < m2) tile[mdst + j] = 0; }
-            }
-            // (3) long matches, whole warp each
-            unsigned longMask = __ballot_sync(FULL, sel && ml > 18);
-            while (longMask) {
-                const int l = __ffs(longMask) - 1;
-                longMask &= longMask - 1;
+            // long matches
+            unsigned m = pendL;
+            while (m) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1;
                 const int s0 = __shfl_sync(FULL, msrc, l);
                 const int d0 = __shfl_sync(FULL, mdst, l);
                 const int len = __shfl_sync(FULL, ml, l);
+                const int sl = __shfl_sync(FULL, srcLen, l);
+                if (!(WAITMODE == 2 || sl == 0 || ready_long(s0, sl))) continue;
+                __threadfence_block();
                 const int off = d0 - s0;
                 if (off == 0)          for (int i = lane; i < len; i += 32) tile[d0 + i] = 0;
                 else if (off >= len)   for (int i = lane; i < len; i += 32) tile[d0 + i] = tile[s0 + i];
                 else                   for (int i = lane; i < len; i += 32) tile[d0 + i] = tile[s0 + (i % off)];
-            }
-        };
-
-        // rounds: copy every match whose source sequences are final, publish, repeat.  Sequences
-        // only ever wait for lower-numbered ones, so the lowest unfinished sequence can always go.
-        __threadfence_block();
-        __syncwarp();                       // this batch's literal stores are visible to all lanes
-        bool pending = hasMatch;
-        unsigned publish = __ballot_sync(FULL, !hasMatch);      // literal-only / padding lanes are final now
-        for (;;) {
-            const bool go = pending && deps_done();
-            const unsigned goMask = __ballot_sync(FULL, go);
-            if (goMask) {
-                __threadfence_block();      // acquire: the flagged sequences' bytes
-                copy_matches(go);
-                pending = pending && !go;
-                publish |= goMask;
-            }
-            if (publish) {
                 __threadfence_block();
                 __syncwarp();
-                if (lane == 0) atomicOr(const_cast<uint32_t*>(&S.done[bt]), publish);
-                publish = 0;
+                publish_long(d0, len);
+                pendL &= ~(1u << l);
+                progress = true;
             }
-            if (!__any_sync(FULL, pending)) break;
-            if (!goMask && WAITMODE == 1) __nanosleep(20);      // nothing was ready: back off
+            if (!__any_sync(FULL, pendS) && !pendL) break;
+            if (!progress && WAITMODE == 1) __nanosleep(20);   // nothing was ready: back off
         }
     }
-
     __syncthreads();
 
     // ---- tile -> global ------------------------------------------------------------------------------
