@@ -266,6 +266,7 @@ decode_copy_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restric
         const int msrc = mdst - offset;
         // bytes actually read: an overlapping match (offset < ml) only reads [msrc, mdst)
         const int srcLen = hasMatch ? (offset == 0 ? 0 : (offset < ml ? offset : ml)) : 0;
+        unsigned backoff = (WAITMODE == 3) ? 64u : 16u;
         bool pendS = hasMatch && ml <= 18;                 // short: lane-parallel
         unsigned pendL = __ballot_sync(FULL, hasMatch && ml > 18);   // long: whole warp, one at a time
         for (;;) {
@@ -325,7 +326,8 @@ decode_copy_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restric
                 progress = true;
             }
             if (!__any_sync(FULL, pendS) && !pendL) break;
-            if (!progress && WAITMODE == 1) __nanosleep(20);   // nothing was ready: back off
+            if (progress) backoff = (WAITMODE == 3) ? 64u : 16u;
+            else if (WAITMODE == 1 || WAITMODE == 3) { __nanosleep(backoff); if (backoff < 512u) backoff <<= 1; }   // nothing ready: back off
         }
     }
     __syncthreads();
@@ -405,6 +407,7 @@ inline int decode_tile_launch(const uint8_t* srcBase, const int64_t* srcOff, con
         switch (variant) {
         case 1: K4_COPY(STAGE_SMALL, 0); K4_COPY(STAGE_BIG, 0); launches += 2; break;
         case 2: K4_COPY(STAGE_SMALL, 2); K4_COPY(STAGE_BIG, 2); launches += 2; break;
+        case 3: K4_COPY(STAGE_SMALL, 3); K4_COPY(STAGE_BIG, 3); launches += 2; break;
         case 9: break;                                     // parse only (timing experiments)
         default: K4_COPY(STAGE_SMALL, 1); K4_COPY(STAGE_BIG, 1); launches += 2; break;
         }
