@@ -193,13 +193,15 @@ struct Slot {          // one in-flight chunk
     int64_t dLo = 0;                  // dst extent origin (direct mode) or 0 (packed mode)
     bool dstPacked = false;
     std::vector<int64_t> packedDstOff;
-    bool busy = false;
+    int64_t dstBytes = 0;             // device-side extent of the destination region of the chunk
+    bool direct = false;              // stage 2 copied straight into the caller's buffer
+    int state = 0;                    // 0 idle, 1 kernel + outLen enqueued, 2 data D2H enqueued
 };
 
 struct DevCtx {
     int dev = -1;
     std::mutex mu;
-    Slot slot[2];
+    Slot slot[3];
     bool init = false;
 };
 
@@ -248,12 +250,42 @@ void scatter_chunk(Op op, const HostArgs& a, Slot& s) {
     });
 }
 
-int finish_slot(Op op, const HostArgs& a, Slot& s) {
-    if (!s.busy) return K4LZ4_OK;
-    s.busy = false;
+// stage 2: the kernel of the chunk has finished -> per-block results to the caller, then the
+// data D2H.  When every block filled its whole slot and the slots are contiguous (the decode
+// case) the bytes go straight into the caller's buffer in one copy; otherwise through the pinned
+// staging buffer and a host-side scatter (stage 3) that leaves bytes >= outLen[i] untouched.
+int stage2_slot(Op op, const HostArgs& a, Slot& s) {
+    if (s.state != 1) return K4LZ4_OK;
     CU_TRY(cudaStreamSynchronize(s.stream));
     memcpy(a.outLen + s.b0, (const int32_t*)s.hMeta.p, sizeof(int32_t) * (size_t)(s.b1 - s.b0));
-    scatter_chunk(op, a, s);
+    s.state = 2;
+    s.direct = false;
+    if (op == OP_USIZE || s.dstBytes <= 0) return K4LZ4_OK;
+    bool full = !s.dstPacked;
+    int64_t sum = 0;
+    for (int64_t i = s.b0; i < s.b1 && full; i++) {
+        const int64_t room = dst_room(op, a, i);
+        full = (int64_t)a.outLen[i] == room;
+        sum += room;
+    }
+    full = full && sum == s.dstBytes;                 // slots tile the extent exactly: no gaps
+    if (full) {
+        s.direct = true;
+        CU_TRY(cudaMemcpyAsync(a.dstBase + s.dLo, s.dDst.p, (size_t)s.dstBytes, cudaMemcpyDeviceToHost, s.stream));
+    } else {
+        CU_TRY(s.hDst.ensure((size_t)s.dstBytes + 16));
+        CU_TRY(cudaMemcpyAsync(s.hDst.p, s.dDst.p, (size_t)s.dstBytes, cudaMemcpyDeviceToHost, s.stream));
+    }
+    return K4LZ4_OK;
+}
+
+// stage 3: data has landed
+int stage3_slot(Op op, const HostArgs& a, Slot& s) {
+    if (s.state == 1) { int rc = stage2_slot(op, a, s); if (rc != K4LZ4_OK) return rc; }
+    if (s.state != 2) return K4LZ4_OK;
+    s.state = 0;
+    CU_TRY(cudaStreamSynchronize(s.stream));
+    if (!s.direct) scatter_chunk(op, a, s);
     return K4LZ4_OK;
 }
 
@@ -292,10 +324,8 @@ int enqueue_chunk(Op op, const HostArgs& a, Slot& s, int64_t b0, int64_t b1) {
     const int64_t srcBytes = srcPacked ? sSum : (sHi - sLo);
     const int64_t dstBytes = dstPacked ? dSum : (dHi - dLo);
     CU_TRY(s.dSrc.ensure((size_t)srcBytes + 16));
-    if (op != OP_USIZE) {
-        CU_TRY(s.dDst.ensure((size_t)dstBytes + 16));
-        CU_TRY(s.hDst.ensure((size_t)dstBytes + 16));
-    }
+    if (op != OP_USIZE) CU_TRY(s.dDst.ensure((size_t)dstBytes + 16));
+    s.dstBytes = (op == OP_USIZE) ? 0 : dstBytes;
     if (dstPacked) s.packedDstOff.resize((size_t)nb);
 
     int64_t sp = 0, dp = 0;
@@ -324,12 +354,10 @@ int enqueue_chunk(Op op, const HostArgs& a, Slot& s, int64_t b0, int64_t b1) {
     DevArgs d{(const uint8_t*)s.dSrc.p, dSrcOff, dSrcLen, (uint8_t*)s.dDst.p, dDstOff, dDstCap,
               dOutLen, (int)nb, a.level};
     CU_TRY(launch_op(op, d, st));
-    if (op != OP_USIZE && dstBytes > 0)
-        CU_TRY(cudaMemcpyAsync(s.hDst.p, s.dDst.p, (size_t)dstBytes, cudaMemcpyDeviceToHost, st));
     // outLen lands at the front of hMeta (offset arrays there are no longer needed once the
     // H2D above has been issued *and completed*; stream order guarantees that)
     CU_TRY(cudaMemcpyAsync(s.hMeta.p, dOutLen, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-    s.busy = true;
+    s.state = 1;
     return K4LZ4_OK;
 }
 
@@ -348,22 +376,28 @@ int run_host_slice(Op op, const HostArgs& a, int64_t b0, int64_t b1, int dev) {
     int rc = K4LZ4_OK;
     int64_t i = b0;
     int c = 0;
+    // three chunks in flight: stage 1 (H2D + kernel + results) of chunk c overlaps stage 2 (data
+    // D2H) of chunk c-1 and stage 3 (host scatter, if needed) of chunk c-2
     while (i < b1) {
         int64_t bytes = 0, j = i;
         while (j < b1 && (j == i || bytes + src_size(a, j) + dst_room(op, a, j) <= CHUNK_BYTES)) {
             bytes += src_size(a, j) + dst_room(op, a, j);
             j++;
         }
-        Slot& s = ctx->slot[c & 1];
-        if ((rc = finish_slot(op, a, s)) != K4LZ4_OK) break;
+        Slot& s = ctx->slot[c % 3];
+        if ((rc = stage3_slot(op, a, s)) != K4LZ4_OK) break;
         if ((rc = enqueue_chunk(op, a, s, i, j)) != K4LZ4_OK) break;
+        if (c >= 1 && (rc = stage2_slot(op, a, ctx->slot[(c - 1) % 3])) != K4LZ4_OK) break;
+        if (c >= 2 && (rc = stage3_slot(op, a, ctx->slot[(c - 2) % 3])) != K4LZ4_OK) break;
         i = j; c++;
     }
-    // drain in issue order
-    int rc2 = finish_slot(op, a, ctx->slot[c & 1]);
-    int rc3 = finish_slot(op, a, ctx->slot[(c + 1) & 1]);
-    if (rc != K4LZ4_OK) { for (auto& s : ctx->slot) { s.busy = false; } cudaDeviceSynchronize(); return rc; }
-    return rc2 != K4LZ4_OK ? rc2 : rc3;
+    if (rc != K4LZ4_OK) { for (auto& s : ctx->slot) s.state = 0; cudaDeviceSynchronize(); return rc; }
+    for (int k = 0; k < 3; k++) {                          // drain in issue order
+        const int idx = ((c - 3 + k) % 3 + 3) % 3;
+        if ((rc = stage3_slot(op, a, ctx->slot[idx])) != K4LZ4_OK) break;
+    }
+    if (rc != K4LZ4_OK) { for (auto& s : ctx->slot) s.state = 0; cudaDeviceSynchronize(); }
+    return rc;
 }
 
 void parallel_for_blocks(int64_t b0, int64_t b1, int64_t bytesHint,
