@@ -1,0 +1,272 @@
+// encode_tile.cuh -- bit-exact LZ4 L00_FAST encoder for blocks below the 64 KiB table limit
+// (n < 65 547: the reference's byU16 case, LL64.fast.cs:526,548), one warp per block with the whole
+// block staged in shared memory.
+//
+// The reference's match search is a serial chain per probe (hash -> slot load -> slot store ->
+// 4-byte compare, LL64.fast.cs:158-234).  Inside one search run the probe POSITIONS do not depend on
+// the data (step = searchMatchNb++ >> 6, :159-170), only the table contents do -- and the only table
+// writes between two probes of a run are the run's own earlier probes.  So a warp evaluates 32
+// consecutive probes at once: every lane hashes its position, loads the slot, and `__match_any_sync`
+// on the hash substitutes the position of the nearest earlier lane with the same hash (= the store
+// the serial code would have done in between).  The first hitting lane wins; lanes up to it commit
+// their slot stores (last writer per hash), later lanes are discarded -- exactly the serial history.
+// The probe right after a match (put ip-2, test ip, LL64.fast.cs:394-466) rides as lane 0 of the
+// next batch.  Common-prefix counting and the backward catch-up are lane-parallel; the block
+// (TMA bulk load) and the 16 KiB u16 table live in shared memory, so the chain never waits on HBM.
+//
+// Reference: /root/reference/src/K4os.Compression.LZ4/Engine/x64/LL64.fast.cs:35-576,
+// Engine/LL.tools.cs:38-51, Engine/x64/LL64.tools.cs:87-133; step numbers = SURVEY.md App. A.
+#pragma once
+#include "common.cuh"
+#include "encode_generic.cuh"
+
+namespace k4 {
+
+constexpr int ENCT_STAGE = 65536 + 64;            // block bytes + alignment slack / read-ahead pad
+constexpr int ENCT_SMEM = ENCT_STAGE + ENC_TABLE_BYTES + 16;
+
+__device__ __forceinline__ uint32_t lds_u32u(const uint8_t* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    return __funnelshift_r(w[0], w[1], (uint32_t)(a & 3) * 8);
+}
+
+// Distance of search probe q from probe 0 of its run.  The reference advances by `step`, then
+// sets step = searchMatchNb++ >> 6 with searchMatchNb starting at 64 (LL64.fast.cs:159-170): the
+// first advance is 1, advance i >= 1 is (63 + i) >> 6, so the first 65 advances are 1, the next 64 are 2, ...
+__device__ __forceinline__ uint32_t probe_advance(uint32_t q) {
+    if (q == 0) return 0;
+    const uint32_t c = 63u + q, k = c >> 6;
+    return 1u + 32u * k * (k - 1u) + (c - 64u * k) * k;
+}
+
+// The encoder proper.  STAGED: the block sits in shared memory at `sin` (sin[p] == src[p]);
+// otherwise positions are read from global memory through L1 (more blocks in flight per SM).
+// Returns the engine's value: bytes written, 0 when the reference's limitedOutput checks fail.
+template <bool STAGED>
+__device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* sin, const uint32_t n,
+                                uint8_t* __restrict__ dst, const int cap, uint16_t* table) {
+    const int lane = lane_id();
+#define RD32(p) (STAGED ? lds_u32u(sin + (p)) : ldg_u32u(src + (p)))
+#define RD8(p) (STAGED ? (uint32_t)sin[(p)] : (uint32_t)__ldg(src + (p)))
+    const bool limited = !(cap >= max_output_size((int)n));                           // LL64.fast.cs:524
+    const int64_t olimit = cap;
+    uint32_t ip = 0, anchor = 0, op = 0;
+
+    if (n >= (uint32_t)MINLENGTH) {                                               // :117
+        const uint32_t mfl1 = n - MFLIMIT + 1, mlim = n - LASTLITERALS;           // :70-71
+        if (lane == 0) table[hash4(RD32(0), 13)] = 0;                       // :120
+        __syncwarp();
+        ip = 1;
+        bool post = false;              // lane 0 of the next batch is the post-match probe at ip
+        uint32_t q0 = 0;                // first search-probe index of the next batch
+        uint32_t base = 1;              // position of search probe 0 of the current run
+        for (;;) {
+            // ---- one batch of up to 32 probes (App. A step 3, and step 8 as lane 0) -----------------
+            uint32_t h2 = 0xFFFFFFFFu;
+            if (post) h2 = hash4(RD32(ip - 2), 13);                     // put(ip-2), :394
+            const bool isPost = post && lane == 0;
+            const uint32_t q = q0 + (uint32_t)lane - (post ? 1u : 0u);            // search-probe index (lanes >= 1 if post)
+            const uint32_t pos = isPost ? ip : base + probe_advance(q);
+            // a search probe executes only if the NEXT probe position stays <= mflimitPlusOne (:172)
+            const bool valid = isPost || (base + probe_advance(q + 1) <= mfl1);
+            const uint32_t v = valid ? RD32(pos) : 0u;
+            const uint32_t h = valid ? hash4(v, 13) : (0x10000u + (uint32_t)lane);
+            uint32_t cand = valid ? (uint32_t)table[h] : 0u;
+            if (h == h2) cand = ip - 2;                                           // sees the put(ip-2)
+            const unsigned peers = __match_any_sync(FULL, h);
+            const unsigned earlier = peers & ((1u << lane) - 1u);
+            const int fromLane = earlier ? 31 - __clz(earlier) : lane;
+            const uint32_t fwdPos = __shfl_sync(FULL, pos, fromLane);
+            if (earlier) cand = fwdPos;                                           // sees the nearest earlier store
+            const bool hit = valid && (RD32(cand) == v);                // :228 (byU16: no distance test)
+            const unsigned hits = __ballot_sync(FULL, hit);
+            const unsigned ends = __ballot_sync(FULL, !valid);
+            const int f = hits ? __ffs(hits) - 1 : 32;
+            const int e = ends ? __ffs(ends) - 1 : 32;
+            if (e < f) break;                                                     // ran into the end: last literals
+            // commit the slot stores of probes 0..f in serial order: last writer per hash wins
+            {
+                const unsigned upto = (f >= 31) ? 0xffffffffu : ((2u << f) - 1u);
+                const unsigned later = peers & ~((2u << lane) - 1u) & upto;       // lanes in (lane, f] with my hash
+                const bool doStore = valid && ((1u << lane) & upto) && !(lane < 31 ? later : 0u);
+                if (post) {
+                    const unsigned same2 = __ballot_sync(FULL, valid && h == h2) & upto;
+                    if (lane == 0 && !same2) table[h2] = (uint16_t)(ip - 2);      // nobody overwrote the put(ip-2)
+                }
+                if (doStore) table[h] = (uint16_t)pos;
+                __syncwarp();
+            }
+            if (f == 32) {                                                        // 32 misses: keep searching
+                if (post) { post = false; base = ip + 1; q0 = 31; }
+                else q0 += 32;
+                continue;
+            }
+            const bool zeroLit = post && f == 0;                                  // :459-463
+            uint32_t m = __shfl_sync(FULL, cand, f);
+            ip = __shfl_sync(FULL, pos, f);
+            if (!zeroLit) {                                                       // step 4: catch-up, :237-242
+                for (;;) {
+                    const bool ok = (ip > anchor + lane) && (m > (uint32_t)lane) &&
+                                    (RD8(ip - 1 - lane) == RD8(m - 1 - lane));
+                    const unsigned bad = __ballot_sync(FULL, !ok);
+                    const int c = bad ? __ffs(bad) - 1 : 32;
+                    ip -= c; m -= c;
+                    if (bad) break;
+                }
+            }
+            // ---- step 5/6: literal run, offset, match length -----------------------------------------
+            const uint32_t lit = ip - anchor;
+            if (!zeroLit && limited && (int64_t)op + 1 + lit + 8 + lit / 255 > olimit) return 0;   // :246-251
+            uint32_t mc = 0;
+            {   // LZ4_count(ip+4, m+4, matchlimit), 4 bytes per lane, :328
+                uint32_t a = ip + MINMATCH + 4u * lane, bb = m + MINMATCH + 4u * lane;
+                for (;;) {
+                    const int room = (int)mlim - (int)a;                          // bytes of this lane below matchlimit
+                    const uint32_t x = room > 0 ? (RD32(a) ^ RD32(bb)) : 0u;
+                    int eq = x ? ((__ffs(x) - 1) >> 3) : 4;
+                    if (eq > room) eq = room < 0 ? 0 : room;
+                    const unsigned stop = __ballot_sync(FULL, eq < 4);
+                    if (stop) {
+                        const int s = __ffs(stop) - 1;
+                        mc += 4u * s + (uint32_t)__shfl_sync(FULL, eq, s);
+                        break;
+                    }
+                    mc += 128; a += 128; bb += 128;
+                }
+            }
+            const uint32_t hdr = run_header_size(lit);
+            const uint32_t afterOff = op + hdr + lit + 2;
+            if (limited && (int64_t)afterOff + 6 + (mc + 240) / 255 > olimit) return 0;   // :332-362
+            // emit: token, literal length bytes, literals, offset, match length bytes
+            {
+                const uint32_t mlTok = mc >= 15 ? 15u : mc;
+                if (lane == 0) {
+                    if (lit >= 15) {
+                        uint32_t o = op, rest = lit - 15;
+                        dst[o++] = (uint8_t)(0xF0 | mlTok);
+                        for (; rest >= 255; rest -= 255) dst[o++] = 255;
+                        dst[o] = (uint8_t)rest;
+                    } else dst[op] = (uint8_t)((lit << 4) | mlTok);
+                    dst[afterOff - 2] = (uint8_t)(ip - m);
+                    dst[afterOff - 1] = (uint8_t)((ip - m) >> 8);
+                }
+                for (uint32_t i = lane; i < lit; i += 32) dst[op + hdr + i] = RD8(anchor + i);
+                op = afterOff;
+                if (mc >= 15) {                                                   // :365-379
+                    const uint32_t rest = mc - 15, nff = rest / 255;
+                    for (uint32_t i = lane; i < nff; i += 32) dst[op + i] = 0xFF;
+                    if (lane == 0) dst[op + nff] = (uint8_t)(rest % 255);
+                    op += nff + 1;
+                }
+            }
+            ip += mc + MINMATCH;
+            anchor = ip;                                                          // :388
+            if (ip >= mfl1) break;                                                // :391
+            post = true; q0 = 0; base = ip + 1;                                   // step 8 rides with the next batch
+        }
+    }
+    {   // ---- step 9: last literals, :469-503 -----------------------------------------------------------
+        const uint32_t run = n - anchor;
+        if (limited && (int64_t)op + run + 1 + (run + 255 - 15) / 255 > olimit) return 0;
+        const uint32_t hdr = run_header_size(run);
+        if (lane == 0) write_run_header(dst, op, run);
+        op += hdr;
+        for (uint32_t i = lane; i < run; i += 32) dst[op + i] = RD8(anchor + i);
+        op += run;
+        return (int)op;
+    }
+#undef RD32
+#undef RD8
+}
+
+__global__ void __launch_bounds__(32)
+encode_tile_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restrict__ srcOff,
+                   const int32_t* __restrict__ srcLen, uint8_t* __restrict__ dstBase,
+                   const int64_t* __restrict__ dstOff, const int32_t* __restrict__ dstCap,
+                   int32_t* __restrict__ outLen, int nBlocks, int level) {
+    extern __shared__ __align__(128) uint8_t smem_enct[];
+    uint8_t* const smem = smem_enct;
+    uint8_t* stage = smem;
+    uint16_t* table = reinterpret_cast<uint16_t*>(smem + ENCT_STAGE);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + ENCT_STAGE + ENC_TABLE_BYTES);
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x;
+    if (b >= nBlocks) return;
+    const int n_ = srcLen[b];
+    const uint8_t* __restrict__ src = srcBase + srcOff[b];
+    uint8_t* __restrict__ dst = dstBase + dstOff[b];
+    const int cap = dstCap[b];
+    if (n_ <= 0) { if (lane == 0) outLen[b] = 0; return; }                       // LZ4Codec.cs:45-46
+    if (level >= 3) { if (lane == 0) outLen[b] = -2; return; }                   // HC/OPT delegate
+    if (n_ >= LIMIT_64K) {                                                        // byU32 case: generic warp encoder
+        const int r = encode_block_warp(src, n_, dst, cap, 0x7fffffff, table, false);
+        if (lane == 0) outLen[b] = r <= 0 ? -1 : r;
+        return;
+    }
+    const uint32_t n = (uint32_t)n_;
+    const int shift = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+    const uint8_t* sin = stage + shift;                                           // sin[p] == src[p]
+
+    // ---- stage the block (TMA bulk, 16 KiB pieces on one mbarrier) and zero the table --------------
+    const int staged = ((int)n + shift + 15) & ~15;
+    if (lane == 0) {
+        const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(a) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(a), "r"(staged) : "memory");
+        for (int off = 0; off < staged; off += 16384) {
+            const int bytes = staged - off < 16384 ? staged - off : 16384;
+            const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(stage + off);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(sdst), "l"(src - shift + off), "r"(bytes), "r"(a) : "memory");
+        }
+    }
+    {
+        uint4* t = reinterpret_cast<uint4*>(table);
+        for (int i = lane; i < ENC_TABLE_BYTES / 16; i += 32) t[i] = make_uint4(0, 0, 0, 0);   // LL.tools.cs:235-239
+    }
+    __syncwarp();
+    {
+        const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+        uint32_t ok;
+        do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(a), "r"(0) : "memory");
+        } while (!ok);
+    }
+
+    const int result = encode_spec_warp<true>(src, sin, n, dst, cap, table);
+    if (lane == 0) outLen[b] = result <= 0 ? -1 : result;                        // LZ4Codec.cs:51
+}
+
+// Global-memory variant: ENC_WARPS_PER_CTA blocks per CTA, only the 16 KiB tables in shared memory.
+__global__ void __launch_bounds__(ENC_WARPS_PER_CTA * 32)
+encode_spec_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restrict__ srcOff,
+                   const int32_t* __restrict__ srcLen, uint8_t* __restrict__ dstBase,
+                   const int64_t* __restrict__ dstOff, const int32_t* __restrict__ dstCap,
+                   int32_t* __restrict__ outLen, int nBlocks, int level) {
+    extern __shared__ __align__(128) uint8_t smem_encs[];
+    const int wInCta = threadIdx.x >> 5;
+    const int b = blockIdx.x * ENC_WARPS_PER_CTA + wInCta;
+    const int lane = lane_id();
+    if (b >= nBlocks) return;
+    uint16_t* table = reinterpret_cast<uint16_t*>(smem_encs + wInCta * ENC_TABLE_BYTES);
+    const int n_ = srcLen[b];
+    const uint8_t* __restrict__ src = srcBase + srcOff[b];
+    uint8_t* __restrict__ dst = dstBase + dstOff[b];
+    const int cap = dstCap[b];
+    if (n_ <= 0) { if (lane == 0) outLen[b] = 0; return; }
+    if (level >= 3) { if (lane == 0) outLen[b] = -2; return; }
+    int r;
+    if (n_ >= LIMIT_64K) r = encode_block_warp(src, n_, dst, cap, 0x7fffffff, table, false);
+    else {
+        uint4* t = reinterpret_cast<uint4*>(table);
+        for (int i = lane; i < ENC_TABLE_BYTES / 16; i += 32) t[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        r = encode_spec_warp<false>(src, nullptr, (uint32_t)n_, dst, cap, table);
+    }
+    if (lane == 0) outLen[b] = r <= 0 ? -1 : r;
+}
+
+}  // namespace k4

@@ -24,6 +24,7 @@
 #include "decode_generic.cuh"
 #include "decode_tile.cuh"
 #include "encode_generic.cuh"
+#include "encode_tile.cuh"
 #include "pickle.cuh"
 #include "synth.cuh"
 #include "copy_blocks.cuh"
@@ -73,6 +74,9 @@ void set_func_attrs(int dev) {
                              k4::ENC_WARPS_PER_CTA * k4::ENC_TABLE_BYTES);
         cudaFuncSetAttribute(k4::pickle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              k4::ENC_WARPS_PER_CTA * k4::ENC_TABLE_BYTES);
+        cudaFuncSetAttribute(k4::encode_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k4::ENCT_SMEM);
+        cudaFuncSetAttribute(k4::encode_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             k4::ENC_WARPS_PER_CTA * k4::ENC_TABLE_BYTES);
         k4::decode_tile_set_attrs();
     });
 }
@@ -90,10 +94,21 @@ cudaError_t launch_op(Op op, const DevArgs& a, cudaStream_t st) {
     set_func_attrs(dev);
     switch (op) {
     case OP_ENCODE: {
-        const int ctas = (a.n + k4::ENC_WARPS_PER_CTA - 1) / k4::ENC_WARPS_PER_CTA;
-        k4::encode_generic_kernel<<<ctas, k4::ENC_WARPS_PER_CTA * 32,
-                                    k4::ENC_WARPS_PER_CTA * k4::ENC_TABLE_BYTES, st>>>(
-            a.srcBase, a.srcOff, a.srcLen, a.dstBase, a.dstOff, a.dstCap, a.outLen, a.n, a.level, 0);
+        static const int encVariant = [] { const char* e = getenv("K4LZ4_ENC_VARIANT"); return e ? atoi(e) : 1; }();
+        if (encVariant == 0) {
+            const int ctas = (a.n + k4::ENC_WARPS_PER_CTA - 1) / k4::ENC_WARPS_PER_CTA;
+            k4::encode_generic_kernel<<<ctas, k4::ENC_WARPS_PER_CTA * 32,
+                                        k4::ENC_WARPS_PER_CTA * k4::ENC_TABLE_BYTES, st>>>(
+                a.srcBase, a.srcOff, a.srcLen, a.dstBase, a.dstOff, a.dstCap, a.outLen, a.n, a.level, 0);
+        } else if (encVariant == 2) {
+            k4::encode_tile_kernel<<<a.n, 32, k4::ENCT_SMEM, st>>>(
+                a.srcBase, a.srcOff, a.srcLen, a.dstBase, a.dstOff, a.dstCap, a.outLen, a.n, a.level);
+        } else {
+            const int ctas = (a.n + k4::ENC_WARPS_PER_CTA - 1) / k4::ENC_WARPS_PER_CTA;
+            k4::encode_spec_kernel<<<ctas, k4::ENC_WARPS_PER_CTA * 32,
+                                     k4::ENC_WARPS_PER_CTA * k4::ENC_TABLE_BYTES, st>>>(
+                a.srcBase, a.srcOff, a.srcLen, a.dstBase, a.dstOff, a.dstCap, a.outLen, a.n, a.level);
+        }
         g_launches++;
         break;
     }
