@@ -45,8 +45,14 @@ __device__ __forceinline__ uint32_t probe_advance(uint32_t q) {
 // Returns the engine's value: bytes written, 0 when the reference's limitedOutput checks fail.
 template <bool STAGED>
 __device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* sin, const uint32_t n,
-                                uint8_t* __restrict__ dst, const int cap, uint16_t* table) {
+                                uint8_t* __restrict__ dst, const int cap, const int hardCap, uint16_t* table) {
     const int lane = lane_id();
+    const int64_t hard = hardCap;       // physical write bound (pickler, see pickle.cuh); 0x7fffffff otherwise
+    {   // LZ4_initStream: zero the table (LL.tools.cs:235-239)
+        uint4* t = reinterpret_cast<uint4*>(table);
+        for (int i = lane; i < ENC_TABLE_BYTES / 16; i += 32) t[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+    }
 #define RD32(p) (STAGED ? lds_u32u(sin + (p)) : ldg_u32u(src + (p)))
 #define RD8(p) (STAGED ? (uint32_t)sin[(p)] : (uint32_t)__ldg(src + (p)))
     const bool limited = !(cap >= max_output_size((int)n));                           // LL64.fast.cs:524
@@ -138,6 +144,7 @@ __device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* 
             const uint32_t hdr = run_header_size(lit);
             const uint32_t afterOff = op + hdr + lit + 2;
             if (limited && (int64_t)afterOff + 6 + (mc + 240) / 255 > olimit) return 0;   // :332-362
+            if ((int64_t)afterOff + (mc >= 15 ? (mc - 15) / 255 + 1 : 0) > hard) return 0;
             // emit: token, literal length bytes, literals, offset, match length bytes
             {
                 const uint32_t mlTok = mc >= 15 ? 15u : mc;
@@ -170,6 +177,7 @@ __device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* 
         const uint32_t run = n - anchor;
         if (limited && (int64_t)op + run + 1 + (run + 255 - 15) / 255 > olimit) return 0;
         const uint32_t hdr = run_header_size(run);
+        if ((int64_t)op + hdr + run > hard) return 0;
         if (lane == 0) write_run_header(dst, op, run);
         op += hdr;
         for (uint32_t i = lane; i < run; i += 32) dst[op + i] = RD8(anchor + i);
@@ -222,10 +230,6 @@ encode_tile_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restric
                          :: "r"(sdst), "l"(src - shift + off), "r"(bytes), "r"(a) : "memory");
         }
     }
-    {
-        uint4* t = reinterpret_cast<uint4*>(table);
-        for (int i = lane; i < ENC_TABLE_BYTES / 16; i += 32) t[i] = make_uint4(0, 0, 0, 0);   // LL.tools.cs:235-239
-    }
     __syncwarp();
     {
         const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
@@ -236,7 +240,7 @@ encode_tile_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restric
         } while (!ok);
     }
 
-    const int result = encode_spec_warp<true>(src, sin, n, dst, cap, table);
+    const int result = encode_spec_warp<true>(src, sin, n, dst, cap, 0x7fffffff, table);
     if (lane == 0) outLen[b] = result <= 0 ? -1 : result;                        // LZ4Codec.cs:51
 }
 
@@ -260,12 +264,7 @@ encode_spec_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restric
     if (level >= 3) { if (lane == 0) outLen[b] = -2; return; }
     int r;
     if (n_ >= LIMIT_64K) r = encode_block_warp(src, n_, dst, cap, 0x7fffffff, table, false);
-    else {
-        uint4* t = reinterpret_cast<uint4*>(table);
-        for (int i = lane; i < ENC_TABLE_BYTES / 16; i += 32) t[i] = make_uint4(0, 0, 0, 0);
-        __syncwarp();
-        r = encode_spec_warp<false>(src, nullptr, (uint32_t)n_, dst, cap, table);
-    }
+    else r = encode_spec_warp<false>(src, nullptr, (uint32_t)n_, dst, cap, 0x7fffffff, table);
     if (lane == 0) outLen[b] = r <= 0 ? -1 : r;
 }
 

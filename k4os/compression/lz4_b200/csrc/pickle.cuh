@@ -13,6 +13,7 @@
 #pragma once
 #include "common.cuh"
 #include "encode_generic.cuh"
+#include "encode_tile.cuh"
 #include "decode_generic.cuh"
 
 namespace k4 {
@@ -41,7 +42,9 @@ __device__ int pickle_message_warp(const uint8_t* __restrict__ src, int n, uint8
     if (n <= 0) return 0;                                        // pickle.cs:54
     if (level >= 3) return -2;                                   // delegate HC/OPT
     const int cap = n <= 1024 ? 1024 : n;                        // :57-67
-    int enc = encode_block_warp(src, n, dst + 2, cap, n - 1, table, false);   // :83
+    int enc = (n < LIMIT_64K)                                                 // :83
+        ? encode_spec_warp<false>(src, nullptr, (uint32_t)n, dst + 2, cap, n - 1, reinterpret_cast<uint16_t*>(table))
+        : encode_block_warp(src, n, dst + 2, cap, n - 1, table, false);
     __syncwarp();
     if (enc <= 0 || enc >= n) {                                  // :85-94
         if (lane == 0) dst[0] = 0;
