@@ -82,6 +82,15 @@ def measured_peak_gbs() -> tuple[float, str]:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def profiled_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (decode_copy_kernel) per
+    launch, from the committed `ncu --set full` capture of this same command (profiles/); null if absent."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["decode_copy_kernel_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -346,6 +355,38 @@ def run_ours(args) -> None:
     except Exception as e:   # noqa: BLE001
         aux["encode_l00_fast"] = {"error": str(e)}
 
+    try:    # configs[3]: LZ4Pickler over small messages (256 B - 4 KiB mixed, seed 42), device-resident
+        pn = 1 << 18
+        prng = np.random.default_rng(42)
+        psz = np.where(prng.random(pn) < 0.5, prng.choice([256, 512, 1024, 2048, 4096], pn),
+                       prng.integers(256, 4097, pn)).astype(np.int32)
+        pofs = np.zeros(pn, dtype=np.int64); pofs[1:] = np.cumsum(psz[:-1], dtype=np.int64)
+        ptot = int(psz.sum())
+        d_po, d_pl = torch.from_numpy(pofs).to(dev), torch.from_numpy(psz).to(dev)
+        pko = np.zeros(pn, dtype=np.int64); pko[1:] = np.cumsum(psz[:-1].astype(np.int64) + 1)
+        d_pko = torch.from_numpy(pko).to(dev)
+        pk = torch.empty(ptot + pn + 16, dtype=torch.uint8, device=dev)
+        pkl = torch.zeros(pn, dtype=torch.int32, device=dev)
+        def p_run():
+            B.pickle_batch_device(dptr(raw), dptr(d_po), dptr(d_pl), dptr(pk), dptr(d_pko), dptr(pkl), pn, 0, stream)
+        pout = torch.empty(ptot + 16, dtype=torch.uint8, device=dev)
+        pol = torch.zeros(pn, dtype=torch.int32, device=dev)
+        def u_run():
+            B.unpickle_batch_device(dptr(pk), dptr(d_pko), dptr(pkl), dptr(pout), dptr(d_po), dptr(d_pl), dptr(pol), pn, stream)
+        res = {}
+        for name, fn in (("pickle", p_run), ("unpickle", u_run)):
+            fn(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ms = a.elapsed_time(b)
+            res[name] = {"Mmsg_per_s": round(pn / ms / 1e3, 2), "GB_per_s": round(ptot / ms / 1e6, 2), "ms": round(ms, 3)}
+        res["verified"] = bool(torch.equal(pout[:ptot], raw[:ptot])) and bool((pol == d_pl).all())
+        res["messages"] = pn
+        res["ratio"] = round(float(pkl.sum()) / ptot, 4)
+        aux["pickler_256B_4KiB"] = res
+    except Exception as e:   # noqa: BLE001
+        aux["pickler_256B_4KiB"] = {"error": str(e)}
+
     # ---- cpu baseline on rank 0 at N = 1 ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -373,7 +414,7 @@ def run_ours(args) -> None:
                        "l2": "inputs (~6 GiB touched per step) >> 126 MB L2; no flush needed",
                        "verified": bool(ok_all)},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None,
+                         "frac": round(achieved / peak, 4), "traffic": profiled_traffic_bytes(),
                          "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": round(kernel_ms, 4),
                          "peak_source": peak_src, "kernel": "k4::decode_parse_kernel + k4::decode_copy_kernel (the two launches of one decode step)"},
             "e2e": {"value": round(e2e_gbs, 3), "unit": "GB/s",

@@ -28,7 +28,7 @@ namespace k4 {
 
 constexpr int SUB_BATCH = 65536;         // blocks per parse/copy kernel pair
 #ifndef K4_COPY_THREADS
-#define K4_COPY_THREADS 512
+#define K4_COPY_THREADS 384
 #endif
 constexpr int COPY_THREADS = K4_COPY_THREADS;
 constexpr int COPY_WARPS = COPY_THREADS / 32;

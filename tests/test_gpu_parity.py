@@ -228,3 +228,80 @@ def test_full_size_roundtrip_property(k4):
     assert torch.equal(out, raw)
     ratio = float(clen.sum()) / (nb * bs)
     assert 0.47 < ratio < 0.53, ratio
+
+
+def test_host_path_all_devices_split_and_scattered_layout(k4, chk):
+    """K4LZ4_ALL_DEVICES (NCCL-free contiguous split over every visible GPU; one device here is the
+    degenerate case) and a scattered, gap-filled layout that forces the packed staging path: results
+    identical to the single-device contiguous call, sentinels between slots untouched."""
+    from k4os.compression.lz4_b200 import _native as N
+    blocks = [inputs.gen(kind, n, i) for i, (kind, n) in enumerate(
+        [("text2", 70000), ("random", 300), ("lorem", 65536), ("synth525", 65536), ("lowent", 4097),
+         ("runs", 20000), ("repeat", 65536), ("text2", 13), ("text2", 12), ("synth435", 131072)] * 3)]
+    ref_enc, ref_len = k4.batch.encode_batch_host(blocks)
+    for i in (0, 3, 9):
+        assert (int(ref_len[i]), ref_enc[i]) == chk.encode(blocks[i])
+    # scattered layout: 4 KiB gaps between source blocks and between destination slots
+    gap = 4096
+    src_len = np.array([len(b) for b in blocks], dtype=np.int32)
+    src_off = np.cumsum(np.concatenate([[gap], src_len[:-1].astype(np.int64) + gap])).astype(np.int64)
+    src = np.full(int(src_off[-1] + src_len[-1] + gap), 0xEE, dtype=np.uint8)
+    for o, b in zip(src_off, blocks):
+        src[o:o + len(b)] = np.frombuffer(b, dtype=np.uint8)
+    cap = np.array([k4.LZ4Codec.MaximumOutputSize(len(b)) for b in blocks], dtype=np.int32)
+    dst_off = np.cumsum(np.concatenate([[gap], cap[:-1].astype(np.int64) + 64 * gap])).astype(np.int64)
+    dst = np.full(int(dst_off[-1] + cap[-1] + gap), 0xCD, dtype=np.uint8)
+    out = k4.batch.encode_batch_flat_host(src, src_off, src_len, dst, dst_off, cap, device=N.ALL_DEVICES)
+    assert out.tolist() == ref_len.tolist()
+    for i, (o, n) in enumerate(zip(dst_off, out)):
+        assert dst[o:o + n].tobytes() == ref_enc[i]
+        assert (dst[o + n:o + cap[i]] == 0xCD).all()
+    # decode the scattered compressed slots back into exact-size slots (direct D2H path) and into
+    # oversized slots (staging + scatter path)
+    for extra in (0, 100):
+        dcap = (src_len + extra).astype(np.int32)
+        doff = np.cumsum(np.concatenate([[0], dcap[:-1].astype(np.int64)])).astype(np.int64)
+        back = np.full(int(dcap.sum()) + 1, 0xCD, dtype=np.uint8)
+        got = k4.batch.decode_batch_flat_host(dst, dst_off, out, back, doff, dcap, device=N.ALL_DEVICES)
+        assert got.tolist() == src_len.tolist()
+        for i, b in enumerate(blocks):
+            assert back[doff[i]:doff[i] + len(b)].tobytes() == b
+            assert (back[doff[i] + len(b):doff[i] + dcap[i]] == 0xCD).all()
+
+
+def test_pickler_batch_at_scale_property(k4):
+    """BASELINE configs[3] shape at 131 072 messages (256 B - 4 KiB mixed): unpickle(pickle(x)) == x,
+    sizes agree, header bytes well-formed; 64 messages compared byte for byte with the oracle."""
+    import torch
+    import oracle
+    port = oracle.Port()
+    B = k4.batch
+    n = 1 << 17
+    rng = np.random.default_rng(42)
+    sizes = np.where(rng.random(n) < 0.5, rng.choice([256, 512, 1024, 2048, 4096], n),
+                     rng.integers(256, 4097, n)).astype(np.int32)
+    off = np.zeros(n, dtype=np.int64); off[1:] = np.cumsum(sizes[:-1], dtype=np.int64)
+    total = int(sizes.sum())
+    dev = torch.device("cuda", 0); st = torch.cuda.current_stream().cuda_stream
+    raw = torch.empty(((total + 65535) // 65536) * 65536, dtype=torch.uint8, device=dev)
+    B.synth_device(raw.data_ptr(), raw.numel() // 65536, 65536, 435, 42, 0, st)
+    d_off, d_len = torch.from_numpy(off).to(dev), torch.from_numpy(sizes).to(dev)
+    poff = np.zeros(n, dtype=np.int64); poff[1:] = np.cumsum(sizes[:-1].astype(np.int64) + 1)
+    d_poff = torch.from_numpy(poff).to(dev)
+    pk = torch.full((int(sizes.sum()) + n + 16,), 0xCD, dtype=torch.uint8, device=dev)
+    plen = torch.zeros(n, dtype=torch.int32, device=dev)
+    B.pickle_batch_device(raw.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), pk.data_ptr(), d_poff.data_ptr(),
+                          plen.data_ptr(), n, 0, st)
+    usz = torch.zeros(n, dtype=torch.int32, device=dev)
+    B.unpickled_size_batch_device(pk.data_ptr(), d_poff.data_ptr(), plen.data_ptr(), usz.data_ptr(), n, st)
+    out = torch.zeros(total + 16, dtype=torch.uint8, device=dev)
+    olen = torch.zeros(n, dtype=torch.int32, device=dev)
+    B.unpickle_batch_device(pk.data_ptr(), d_poff.data_ptr(), plen.data_ptr(), out.data_ptr(), d_off.data_ptr(),
+                            d_len.data_ptr(), olen.data_ptr(), n, st)
+    torch.cuda.synchronize()
+    assert bool((usz == d_len).all()) and bool((olen == d_len).all())
+    assert torch.equal(out[:total], raw[:total])
+    assert bool((plen <= d_len + 1).all()) and bool((plen > 0).all())
+    h_raw, h_pk, h_pl = raw[:int(off[64])].cpu().numpy(), pk[:int(poff[64])].cpu().numpy(), plen[:64].cpu().numpy()
+    for i in range(64):
+        assert h_pk[poff[i]:poff[i] + h_pl[i]].tobytes() == port.pickle(h_raw[off[i]:off[i] + sizes[i]].tobytes()), i
