@@ -45,8 +45,6 @@ constexpr int PR_G = 8;                  // commit groups (= steps) a copy is gi
 // the same four banks (32-way conflict, measured: half of all stall samples); 272 = 68 words spreads
 // eight lanes over the 32 banks, the minimum for a 512-byte warp access.
 constexpr int PR_STRIDE = PR_RING + 16;
-constexpr int PR_PF_BYTES = 1024;        // bytes per L2 bulk prefetch
-constexpr int PR_PF_AHEAD = 1024;        // issue the next one when the read position is this close to its start
 
 enum ParseState : int { PS_TOKEN = 0, PS_LITVLE, PS_LITEND, PS_OFFSET, PS_MATCHVLE, PS_MATCHCHK, PS_SEQEND,
                         PS_FINAL_OK, PS_FINAL_ERR, PS_FINAL_FALLBACK };
@@ -82,7 +80,6 @@ decode_parse_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restri
     const int iend = n, oend = cap;
     const int shortiend = iend - 16, shortoend = oend - 32;                                  // :152-153
     int req = 0;                      // next 16-byte chunk to request (absolute index from gbase)
-    int pfB = 0;                      // bytes (from gbase) already asked into L2 by bulk prefetches
     int nseq = 0, result = -1;
     int tokPos = 0, seqOut = 0, len = 0, match = 0;
     uint32_t token = 0;
@@ -92,16 +89,6 @@ decode_parse_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restri
 #define PR_RD(pos) ((uint32_t)ring[PR_A(pos) & (PR_RING - 1)])
 
     while (__any_sync(FULL, state < PS_FINAL_OK)) {
-        // ---- DRAM-friendly lookahead: 65 536 lanes each pulling 16 bytes at a time from their own
-        // stream is a random 32-byte access pattern for HBM (measured: 0.5 TB/s, 11 us per copy).  So
-        // every lane asks for its stream 1 KiB at a time into L2 (cp.async.bulk.prefetch.L2), one to
-        // two KiB ahead of its read position; the 16-byte ring copies below then hit L2.
-        if (state < PS_FINAL_OK && PR_A(ip) + PR_PF_AHEAD > pfB && pfB < (nChunks << 4)) {
-            int bytes = (nChunks << 4) - pfB;
-            if (bytes > PR_PF_BYTES) bytes = PR_PF_BYTES;
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(gbase + pfB), "r"(bytes) : "memory");
-            pfB += PR_PF_BYTES;
-        }
         // ---- keep the ring filled: at most one 16-byte copy per step per lane -------------------
         const int curChunk = PR_A(ip) >> 4;
         if (req < curChunk) req = curChunk;                   // jumped over a long literal run

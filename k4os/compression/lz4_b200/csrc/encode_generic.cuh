@@ -212,7 +212,7 @@ __device__ __forceinline__ int codec_encode_warp(const uint8_t* src, int n, uint
     return r <= 0 ? -1 : r;
 }
 
-constexpr int ENC_WARPS_PER_CTA = 4;
+constexpr int ENC_WARPS_PER_CTA = 7;   // 7 x 16 KiB tables = 112 KiB: two CTAs (14 blocks in flight) per SM
 
 __global__ void __launch_bounds__(ENC_WARPS_PER_CTA * 32)
 encode_generic_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restrict__ srcOff,
