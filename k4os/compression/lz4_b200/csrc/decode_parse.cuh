@@ -37,6 +37,9 @@ struct BlockInfo {
     int32_t lastIsTerminal;   // the last descriptor is the final literal-only sequence
 };
 
+#ifndef K4_PARSE_BULK
+#define K4_PARSE_BULK 1
+#endif
 constexpr int PARSE_THREADS = 128;
 constexpr int PR_RING = 256;             // bytes of ring per lane
 constexpr int PR_NCH = PR_RING / 16;     // 16-byte chunks per ring
@@ -55,6 +58,9 @@ decode_parse_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restri
                     int32_t* __restrict__ outLen, BlockInfo* __restrict__ info,
                     uint32_t* __restrict__ descs, int first, int count) {
     __shared__ __align__(16) uint8_t rings[PARSE_THREADS * PR_STRIDE];
+#if K4_PARSE_BULK
+    __shared__ unsigned long long bars[PARSE_THREADS * 2];   // one mbarrier per 128-byte ring half per lane
+#endif
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = t < count;
     const int b = first + (live ? t : 0);
@@ -72,14 +78,18 @@ decode_parse_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restri
     uint32_t* __restrict__ d = descs + (size_t)(live ? t : 0) * DESC_CAP;
     const int shift = (int)(reinterpret_cast<uintptr_t>(src) & 15);
     const uint8_t* gbase = src - shift;                       // 16-byte aligned
+#if !K4_PARSE_BULK
     const int nChunks = (n + shift + 15) >> 4;
+#endif
     uint8_t* ring = rings + threadIdx.x * PR_STRIDE;
     const uint32_t ringS = (uint32_t)__cvta_generic_to_shared(ring);
 
     int ip = 0, op = 0;
     const int iend = n, oend = cap;
     const int shortiend = iend - 16, shortoend = oend - 32;                                  // :152-153
+#if !K4_PARSE_BULK
     int req = 0;                      // next 16-byte chunk to request (absolute index from gbase)
+#endif
     int nseq = 0, result = -1;
     int tokPos = 0, seqOut = 0, len = 0, match = 0;
     uint32_t token = 0;
@@ -88,7 +98,54 @@ decode_parse_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restri
 #define PR_A(pos) ((pos) + shift)
 #define PR_RD(pos) ((uint32_t)ring[PR_A(pos) & (PR_RING - 1)])
 
+#if K4_PARSE_BULK
+    // Ring = two 128-byte halves, each filled by ONE bulk copy (cp.async.bulk global -> shared: a whole
+    // line per request instead of eight scattered 16-byte pieces) that completes on the lane's own
+    // mbarrier; a lane polls its barriers without blocking and idles for a step when the bytes it
+    // needs have not landed.  Invariant: at most two halves in flight, on alternating slots, and a
+    // slot is only re-armed after its previous copy has been OBSERVED complete (hReq - hRdy < 2).
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&bars[threadIdx.x * 2]);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar0) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar0 + 8) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const int stagedEnd = (n + shift + 15) & ~15;             // bytes worth fetching, from gbase
+    int hReq = 0;                     // next 128-byte half to request (absolute index from gbase)
+    int hRdy = 0;                     // halves [.., hRdy) are known to have landed (hRdy <= hReq)
+    uint32_t phase = 0;               // bit s: parity of the next completion to wait for on slot s
+#endif
     while (__any_sync(FULL, state < PS_FINAL_OK)) {
+#if K4_PARSE_BULK
+        int rdyEnd;
+        {
+            const int curHalf = PR_A(ip) >> 7;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {                           // landed?  oldest first
+                if (hRdy < hReq) {
+                    const int slot = hRdy & 1;
+                    uint32_t okk;
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                                 "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(okk) : "r"(bar0 + 8u * slot), "r"((phase >> slot) & 1u) : "memory");
+                    if (okk) { hRdy++; phase ^= 1u << slot; }
+                }
+            }
+            // jumped past everything requested (long literal run): once nothing is in flight, restart
+            // at the half holding ip
+            if (curHalf >= hReq && hRdy == hReq) hReq = hRdy = curHalf;
+            if (state < PS_FINAL_OK && hReq >= curHalf && hReq <= curHalf + 1 && hReq - hRdy < 2 &&
+                (hReq << 7) < stagedEnd) {
+                int bytes = stagedEnd - (hReq << 7);
+                if (bytes > 128) bytes = 128;
+                const int slot = hReq & 1;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar0 + 8u * slot), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(ringS + 128u * slot), "l"(gbase + ((size_t)hReq << 7)), "r"(bytes), "r"(bar0 + 8u * slot) : "memory");
+                hReq++;
+            }
+            rdyEnd = (hRdy << 7) < stagedEnd ? (hRdy << 7) : (stagedEnd + 4096);
+            if (hRdy <= curHalf) rdyEnd = 0;                        // the half holding ip itself is not there yet
+        }
+#else
         // ---- keep the ring filled: at most one 16-byte copy per step per lane -------------------
         const int curChunk = PR_A(ip) >> 4;
         if (req < curChunk) req = curChunk;                   // jumped over a long literal run
@@ -102,6 +159,7 @@ decode_parse_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restri
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group %0;" :: "n"(PR_G) : "memory");
         const int rdyEnd = (req - PR_G) << 4;                 // absolute byte bound of landed data
+#endif
 #define PR_READY(pos, k) (PR_A(pos) + (k) <= rdyEnd)
 
         // ---- fast path: the ordinary sequence (lengths with at most two extension bytes), nothing
@@ -208,7 +266,17 @@ decode_parse_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restri
             else { d[nseq++] = (uint32_t)tokPos | ((uint32_t)seqOut << 16); state = PS_TOKEN; }
         }
     }
+#if K4_PARSE_BULK
+    while (hRdy < hReq) {                                     // drain the bulk copies still in flight
+        const int slot = hRdy & 1;
+        uint32_t okk;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(okk) : "r"(bar0 + 8u * slot), "r"((phase >> slot) & 1u) : "memory");
+        if (okk) { hRdy++; phase ^= 1u << slot; }
+    }
+#else
     asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
 #undef PR_A
 #undef PR_RD
 #undef PR_READY
