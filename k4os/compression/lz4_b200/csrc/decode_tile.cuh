@@ -64,8 +64,8 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
     } while (!ok);
 }
 
-// WAITMODE: 0 = spin, 1 = spin with nanosleep back-off, 2 = no waiting (timing experiments only)
-template <int STAGE, int WAITMODE, int PASSES>
+// WAITMODE: 1 = poll with nanosleep back-off (product); 2 = no waiting (timing experiments only: wrong output)
+template <int STAGE, int WAITMODE>
 __global__ void __launch_bounds__(COPY_THREADS, (COPY_THREADS <= 512 ? 2 : 1))
 decode_copy_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restrict__ srcOff,
                    const int32_t* __restrict__ srcLen, uint8_t* __restrict__ dstBase,
@@ -128,12 +128,6 @@ decode_copy_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restric
 
     // ---- batches: one sequence per lane -----------------------------------------------------------
     int piecesSeen = 0;                                   // staged pieces this warp has waited for
-    // PASSES == 2: pass 0 copies every literal run of the block (no dependencies at all), pass 1
-    // the matches -- then only match -> match dependencies are left to wait for.
-    for (int pass = 0; pass < PASSES; pass++) {
-    const bool doLits = (PASSES == 1) || pass == 0;
-    const bool doMatches = (PASSES == 1) || pass == 1;
-    if (pass == 1) __syncthreads();
     uint32_t descNext = (warp < nbatch && warp * 32 + lane < nseq) ? __ldg(d + warp * 32 + lane) : 0u;
     for (int bt = warp; bt < nbatch; bt += COPY_WARPS) {
         const int k = bt * 32 + lane;
@@ -231,7 +225,7 @@ decode_copy_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restric
         };
 
         // ---- literals: short runs lane-parallel (all loads, then all stores), long runs by the warp -----
-        if (doLits) {
+        {
             const int shortLit = lit < 15 ? lit : 0;
             const int mx = __reduce_max_sync(FULL, shortLit);
             if (mx > 0) {
@@ -269,9 +263,9 @@ decode_copy_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restric
         const int msrc = mdst - offset;
         // bytes actually read: an overlapping match (offset < ml) only reads [msrc, mdst)
         const int srcLen = hasMatch ? (offset == 0 ? 0 : (offset < ml ? offset : ml)) : 0;
-        unsigned backoff = (WAITMODE == 3) ? 64u : 16u;
-        bool pendS = doMatches && hasMatch && ml <= 18;    // short: lane-parallel
-        unsigned pendL = __ballot_sync(FULL, doMatches && hasMatch && ml > 18);   // long: whole warp, one at a time
+        unsigned backoff = 16u;
+        bool pendS = hasMatch && ml <= 18;                 // short: lane-parallel
+        unsigned pendL = __ballot_sync(FULL, hasMatch && ml > 18);   // long: whole warp, one at a time
         for (;;) {
             bool progress = false;
             // short matches whose source bytes are all final
@@ -329,10 +323,9 @@ decode_copy_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restric
                 progress = true;
             }
             if (!__any_sync(FULL, pendS) && !pendL) break;
-            if (progress) backoff = (WAITMODE == 3) ? 64u : 16u;
-            else if (WAITMODE == 1 || WAITMODE == 3) { __nanosleep(backoff); if (backoff < 512u) backoff <<= 1; }   // nothing ready: back off
+            if (progress) backoff = 16u;
+            else if (WAITMODE == 1) { __nanosleep(backoff); if (backoff < 512u) backoff <<= 1; }   // nothing ready: back off
         }
-    }
     }
     __syncthreads();
 
@@ -361,18 +354,18 @@ decode_copy_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restric
 // ------------------------------------------------------------------------------------------------
 // launcher
 // ------------------------------------------------------------------------------------------------
-template <int STAGE, int W, int P>
+template <int STAGE, int W>
 inline void decode_copy_launch_t(const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen,
                                  uint8_t* dstBase, const int64_t* dstOff, const int32_t* dstCap,
                                  int32_t* outLen, const BlockInfo* info, const uint32_t* descs,
                                  int first, int count, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(decode_copy_kernel<STAGE, W, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(decode_copy_kernel<STAGE, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(CopySmem<STAGE>));
         attr = true;
     }
-    decode_copy_kernel<STAGE, W, P><<<count, COPY_THREADS, sizeof(CopySmem<STAGE>), st>>>(
+    decode_copy_kernel<STAGE, W><<<count, COPY_THREADS, sizeof(CopySmem<STAGE>), st>>>(
         srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, info, descs, first);
 }
 
@@ -407,13 +400,11 @@ inline int decode_tile_launch(const uint8_t* srcBase, const int64_t* srcOff, con
         decode_parse_kernel<<<(count + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(
             srcBase, srcOff, srcLen, dstCap, outLen, info, descs, first, count);
         launches++;
-#define K4_COPY(STG, W, P) decode_copy_launch_t<STG, W, P>(srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, info, descs, first, count, st)
+#define K4_COPY(STG, W) decode_copy_launch_t<STG, W>(srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, info, descs, first, count, st)
         switch (variant) {
-        case 1: K4_COPY(STAGE_SMALL, 1, 2); K4_COPY(STAGE_BIG, 1, 2); launches += 2; break;   // literals pass, then matches pass
-        case 2: K4_COPY(STAGE_SMALL, 2, 1); K4_COPY(STAGE_BIG, 2, 1); launches += 2; break;
-        case 3: K4_COPY(STAGE_SMALL, 2, 2); K4_COPY(STAGE_BIG, 2, 2); launches += 2; break;
-        case 9: break;                                     // parse only (timing experiments)
-        default: K4_COPY(STAGE_SMALL, 1, 1); K4_COPY(STAGE_BIG, 1, 1); launches += 2; break;
+        case 2: K4_COPY(STAGE_SMALL, 2); K4_COPY(STAGE_BIG, 2); launches += 2; break;   // no waiting (tools/dbench.py only)
+        case 9: break;                                                                   // parse only (tools/dbench.py only)
+        default: K4_COPY(STAGE_SMALL, 1); K4_COPY(STAGE_BIG, 1); launches += 2; break;
         }
 #undef K4_COPY
     }
