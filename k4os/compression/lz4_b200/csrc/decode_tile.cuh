@@ -359,11 +359,13 @@ inline void decode_copy_launch_t(const uint8_t* srcBase, const int64_t* srcOff, 
                                  uint8_t* dstBase, const int64_t* dstOff, const int32_t* dstCap,
                                  int32_t* outLen, const BlockInfo* info, const uint32_t* descs,
                                  int first, int count, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {false};                       // function attributes are per device
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!attr[dev]) {
         cudaFuncSetAttribute(decode_copy_kernel<STAGE, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(CopySmem<STAGE>));
-        attr = true;
+        attr[dev] = true;
     }
     decode_copy_kernel<STAGE, W><<<count, COPY_THREADS, sizeof(CopySmem<STAGE>), st>>>(
         srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, info, descs, first);
