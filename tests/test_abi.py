@@ -65,3 +65,33 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dp, f), errors="replace").read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "k4lz4_oracle" not in text and "libk4ref" not in text, f
+
+
+def test_cpp_mirror_header_compiles_and_links(native, tmp_path):
+    """include/k4lz4.hpp (the compiled-language host mirror of LZ4Codec / LZ4Pickler) builds against
+    the C ABI with a plain host compiler and resolves against libk4lz4.so."""
+    import shutil
+    import subprocess
+    from k4os.compression.lz4_b200 import _native
+    gxx = shutil.which("g++")
+    if gxx is None:
+        import pytest
+        pytest.skip("no g++")
+    src = tmp_path / "t.cpp"
+    src.write_text(
+        '#include "k4lz4.hpp"\n'
+        'int main() {\n'
+        '  using namespace k4lz4;\n'
+        '  if (LZ4Codec::MaximumOutputSize(65536) != 65809) return 1;\n'
+        '  if (LZ4Codec::Version != 192) return 2;\n'
+        '  unsigned char b[4] = {0};\n'
+        '  if (LZ4Codec::Encode(b, 0, b, 4) != 0) return 3;          // empty input -> 0, no device needed\n'
+        '  if (LZ4Codec::Decode(b, 0, b, 4) != 0) return 4;\n'
+        '  if (!LZ4Pickler::Pickle(b, 0).empty()) return 5;\n'
+        '  return (int)LZ4Level::L12_MAX == 12 ? 0 : 6;\n'
+        '}\n')
+    exe = tmp_path / "t"
+    libdir = os.path.dirname(_native.SO_PATH)
+    subprocess.run([gxx, "-std=c++17", "-I", os.path.join(ROOT, "include"), str(src), "-L", libdir, "-lk4lz4",
+                    f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True, capture_output=True)
+    assert subprocess.run([str(exe)]).returncode == 0
