@@ -55,6 +55,21 @@ class _Harness:
             C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
             C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
 
+    _datagen_sym = "k4o_datagen"
+
+    def datagen(self, size: int, match_proba: float, lit_proba: float = 0.0, seed: int = 1234,
+                out: np.ndarray | None = None) -> np.ndarray:
+        """RDG_genBuffer(buf, size, matchProba, litProba, seed) of orig/programs/datagen.c:156-162
+        (0.63 -> configs[1], 0.55 -> configs[2]).  One serial stream."""
+        fn = getattr(self._lib, self._datagen_sym)
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.c_double, C.c_uint32]
+        buf = out if out is not None else np.empty(size, dtype=np.uint8)
+        assert buf.dtype == np.uint8 and buf.size >= size and buf.flags.c_contiguous
+        if fn(buf.ctypes.data, size, float(match_proba), float(lit_proba), int(seed)) != 0:
+            raise ValueError("datagen: bad arguments")
+        return buf
+
     def run_batch(self, mode, src, src_off, src_len, dst, dst_off, dst_cap, out_len, threads):
         """mode 0 = encode, 1 = decode.  All arrays numpy (u8 / i64 / i32).  Returns seconds."""
         n = int(src_len.shape[0])
@@ -138,6 +153,7 @@ class Port(_Harness):
 class Ref(_Harness):
     """The reference's own upstream C engine (orig/lib/lz4.c), LZ4Codec post-processing applied."""
     kind = "reference"
+    _datagen_sym = "k4ref_datagen"
 
     def __init__(self):
         if not os.path.exists(REF_SO):

@@ -30,6 +30,11 @@ int k4ref_compress_fast(const uint8_t *s, int n, uint8_t *d, int cap)
 int k4ref_decompress_safe(const uint8_t *s, int n, uint8_t *d, int cap)
 { return LZ4_decompress_safe((const char *)s, (char *)d, n, cap); }
 int k4ref_version(void) { return LZ4_versionNumber(); }
+/* the reference's own synthetic-data generator (orig/programs/datagen.c:156-162), SURVEY 8(d) */
+#include <stddef.h>
+void RDG_genBuffer(void *buffer, size_t size, double matchProba, double litProba, unsigned seed);
+int k4ref_datagen(uint8_t *buf, size_t size, double matchProba, double litProba, unsigned seed)
+{ if (!buf || matchProba >= 1.0) return -1; RDG_genBuffer(buf, size, matchProba, litProba, seed); return 0; }
 #else
 #include "k4lz4_oracle.h"
 static int enc_one(const uint8_t *s, int n, uint8_t *d, int cap)

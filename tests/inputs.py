@@ -87,3 +87,38 @@ def mutate(stream: bytes, rng: np.random.Generator) -> bytes:
         i = int(rng.integers(0, len(c) - 2))
         c[i + 1] = 0; c[i + 2] = 0          # plant a zero offset somewhere
     return bytes(c)
+
+
+def uses_zero_offset(stream: bytes) -> bool:
+    """True iff the token chain of `stream` contains a match with offset 0 (or cannot be walked).
+
+    The reference accepts such a match -- `match == op >= dst` passes LL64.dec.cs:338 -- and copies
+    whatever the destination buffer held before, so the CONTENT of the decoded block is unspecified
+    (only the returned length is contractual).  Content comparisons skip exactly these streams; a
+    plain `b"\x00\x00" in stream` test would also skip every stream with two zero literals."""
+    c = bytes(stream)
+    n = len(c)
+    p = 0
+    try:
+        while p < n:
+            t = c[p]; p += 1
+            lit = t >> 4
+            if lit == 15:
+                while True:
+                    s = c[p]; p += 1; lit += s
+                    if s != 255:
+                        break
+            p += lit
+            if p + 2 > n:
+                return False
+            if c[p] == 0 and c[p + 1] == 0:
+                return True
+            p += 2
+            if (t & 15) == 15:
+                while True:
+                    s = c[p]; p += 1
+                    if s != 255:
+                        break
+        return False
+    except IndexError:
+        return True

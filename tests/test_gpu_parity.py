@@ -101,7 +101,7 @@ def test_decode_malformed_matches_oracle(k4):
     for i, (c, cap) in enumerate(zip(streams, caps)):
         r, ref = port.decode(c, cap)
         assert int(got[i]) == r, (i, cap, int(got[i]), r)
-        if r > 0 and b"\x00\x00" not in c:
+        if r > 0 and not inputs.uses_zero_offset(c):      # offset-0 content is unspecified
             assert dec[i] == ref, i
 
 
