@@ -38,6 +38,28 @@ namespace K4os.Compression.LZ4.Engine.Native
             byte* srcBase, long* srcOff, int* srcLen, byte* dstBase, long* dstOff, int* dstLen,
             int* outLen, int nMessages, int memKind, void* cudaStream, int device);
 
+        // decode with an external dictionary / partial decode (LZ4Codec.cs:123-134,144-157)
+        [DllImport(Lib)] public static extern int k4lz4_decode_dict(
+            byte* src, int srcLen, byte* dst, int dstCap, byte* dict, int dictLen);
+        [DllImport(Lib)] public static extern int k4lz4_partial_decode(byte* src, int srcLen, byte* dst, int targetLen);
+        [DllImport(Lib)] public static extern int k4lz4_decode_dict_batch(
+            byte* srcBase, long* srcOff, int* srcLen, byte* dstBase, long* dstOff, int* dstCap,
+            byte* dictBase, long* dictOff, int* dictLen, int* outLen, int nBlocks,
+            int memKind, void* cudaStream, int device);
+        [DllImport(Lib)] public static extern int k4lz4_partial_decode_batch(
+            byte* srcBase, long* srcOff, int* srcLen, byte* dstBase, long* dstOff, int* targetLen,
+            int* outLen, int nBlocks, int memKind, void* cudaStream, int device);
+        // LL.Enforce32 semantics (LL.tools.cs:29-36) for inputs >= 65 547 bytes
+        [DllImport(Lib)] public static extern int k4lz4_encode_x32(byte* src, int srcLen, byte* dst, int dstCap, int level);
+        [DllImport(Lib)] public static extern int k4lz4_encode_batch_x32(
+            byte* srcBase, long* srcOff, int* srcLen, byte* dstBase, long* dstOff, int* dstCap,
+            int* outLen, int nBlocks, int level, int memKind, void* cudaStream, int device);
+        // Pickle<TBufferWriter> (LZ4Pickler.pickle.cs:113-148)
+        [DllImport(Lib)] public static extern int k4lz4_pickle_writer_bound(int length);
+        [DllImport(Lib)] public static extern int k4lz4_pickle_writer_batch(
+            byte* srcBase, long* srcOff, int* srcLen, byte* dstBase, long* dstOff,
+            int* outLen, int nMessages, int level, int memKind, void* cudaStream, int device);
+
         public static string LastError() => new string(k4lz4_last_error());
     }
 }

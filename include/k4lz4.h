@@ -100,10 +100,57 @@ K4LZ4_API int32_t k4lz4_encode_batch(const uint8_t *srcBase, const int64_t *srcO
                                      int32_t *outLen, int32_t nBlocks, int32_t level,
                                      int32_t memKind, void *cudaStream, int32_t device);
 
+/* The same two calls with the reference's global LL.Enforce32 switch set (Engine/LL.tools.cs:29-36,
+ * LZ4Codec.cs:21-25): the 32-bit engine LL32.  Its output differs from LL64's only for inputs of
+ * >= 65 547 bytes (4 096-entry u32 table with hash4 instead of hash5, LL64.tools.cs:135-143 vs
+ * LL32); below that both engines emit identical bytes and these calls equal the plain ones. */
+K4LZ4_API int32_t k4lz4_encode_x32(const uint8_t *src, int32_t srcLen, uint8_t *dst, int32_t dstCap, int32_t level);
+K4LZ4_API int32_t k4lz4_encode_batch_x32(const uint8_t *srcBase, const int64_t *srcOff, const int32_t *srcLen,
+                                         uint8_t *dstBase, const int64_t *dstOff, const int32_t *dstCap,
+                                         int32_t *outLen, int32_t nBlocks, int32_t level,
+                                         int32_t memKind, void *cudaStream, int32_t device);
+
 K4LZ4_API int32_t k4lz4_decode_batch(const uint8_t *srcBase, const int64_t *srcOff, const int32_t *srcLen,
                                      uint8_t *dstBase, const int64_t *dstOff, const int32_t *dstCap,
                                      int32_t *outLen, int32_t nBlocks,
                                      int32_t memKind, void *cudaStream, int32_t device);
+
+/* ---- decode with an external dictionary, partial decode ------------ */
+
+/* LZ4Codec.Decode(byte*,int,byte*,int,byte*,int) -- LZ4Codec.cs:144-157; replaces the call to
+ * LLxx.LZ4_decompress_safe_usingDict (Engine/LLxx.cs:42-52, Engine/x64/LL64.dec.cs:523-546).
+ * Matches may reach back into `dict` (the bytes logically preceding the block).  Host pointers. */
+K4LZ4_API int32_t k4lz4_decode_dict(const uint8_t *src, int32_t srcLen, uint8_t *dst, int32_t dstCap,
+                                    const uint8_t *dict, int32_t dictLen);
+
+/* LZ4Codec.PartialDecode(byte*,int,byte*,int) -- LZ4Codec.cs:123-134; replaces the call to
+ * LLxx.LZ4_decompress_safe_partial (Engine/LLxx.cs:29-39): decoding stops at targetLen bytes. */
+K4LZ4_API int32_t k4lz4_partial_decode(const uint8_t *src, int32_t srcLen, uint8_t *dst, int32_t targetLen);
+
+/* Batched forms; block i uses dictBase[dictOff[i] .. +dictLen[i]) (dictBase may be NULL: no
+ * dictionaries).  Same memKind / stream / device conventions as k4lz4_decode_batch, except that
+ * memKind == K4LZ4_MEM_HOST runs on one GPU (`device`, K4LZ4_ALL_DEVICES = GPU 0).  These are the
+ * exact warp-per-block engine (decode_generic.cuh), not the tile kernel. */
+K4LZ4_API int32_t k4lz4_decode_dict_batch(const uint8_t *srcBase, const int64_t *srcOff, const int32_t *srcLen,
+                                          uint8_t *dstBase, const int64_t *dstOff, const int32_t *dstCap,
+                                          const uint8_t *dictBase, const int64_t *dictOff, const int32_t *dictLen,
+                                          int32_t *outLen, int32_t nBlocks,
+                                          int32_t memKind, void *cudaStream, int32_t device);
+K4LZ4_API int32_t k4lz4_partial_decode_batch(const uint8_t *srcBase, const int64_t *srcOff, const int32_t *srcLen,
+                                             uint8_t *dstBase, const int64_t *dstOff, const int32_t *targetLen,
+                                             int32_t *outLen, int32_t nBlocks,
+                                             int32_t memKind, void *cudaStream, int32_t device);
+
+/* ---- XXH32: the checksum of the LZ4 Frame container ------------------------ */
+
+/* XXH32 of one buffer on the host (frame header byte, serial content checksum) --
+ * Streams/Frames/LZ4FrameWriter.cs:100,162-181 via K4os.Hash.xxHash; orig/lib/xxhash.c. */
+K4LZ4_API uint32_t k4lz4_xxh32(const uint8_t *data, int64_t length, uint32_t seed);
+/* XXH32 of every block of a batch on the GPU (per-block checksums, LZ4FrameWriter.cs:169-175):
+ * out[i] = XXH32(base[off[i] .. +len[i]), seed). */
+K4LZ4_API int32_t k4lz4_xxh32_batch(const uint8_t *base, const int64_t *off, const int32_t *len, uint32_t seed,
+                                    uint32_t *out, int32_t nBlocks,
+                                    int32_t memKind, void *cudaStream, int32_t device);
 
 /* ---- LZ4Pickler, byte[] variant, batched ----------------------------------------------- */
 
@@ -118,6 +165,17 @@ K4LZ4_API int32_t k4lz4_pickle_batch(const uint8_t *srcBase, const int64_t *srcO
                                      uint8_t *dstBase, const int64_t *dstOff,
                                      int32_t *outLen, int32_t nMessages, int32_t level,
                                      int32_t memKind, void *cudaStream, int32_t device);
+
+/* LZ4Pickler.Pickle<TBufferWriter>(ReadOnlySpan<byte>, writer, level) -- LZ4Pickler.pickle.cs:113-148.
+ * Different bytes than the byte[] variant: the header width is chosen from the full length before
+ * encoding (:129,161-165) and the payload is encoded with capacity n (:130-133).  Message i ->
+ * dstBase[dstOff[i] ..), which must hold k4lz4_pickle_writer_bound(srcLen[i]) bytes (what the
+ * reference asks its writer for); outLen[i] = bytes the reference would Advance() the writer by. */
+K4LZ4_API int32_t k4lz4_pickle_writer_bound(int32_t length);
+K4LZ4_API int32_t k4lz4_pickle_writer_batch(const uint8_t *srcBase, const int64_t *srcOff, const int32_t *srcLen,
+                                            uint8_t *dstBase, const int64_t *dstOff,
+                                            int32_t *outLen, int32_t nMessages, int32_t level,
+                                            int32_t memKind, void *cudaStream, int32_t device);
 
 /* LZ4Pickler.UnpickledSize(ReadOnlySpan<byte>) -- LZ4Pickler.unpickle.cs:83-92,131-148.
  * outSize[i] = unpickled size, or K4LZ4_R_CORRUPT where the reference throws. */
@@ -161,6 +219,12 @@ K4LZ4_API int32_t k4lz4_copy_blocks_device(const uint8_t *srcBase, const int64_t
 
 /* Counters for bench.py: number of kernels this library has launched since load. */
 K4LZ4_API int64_t k4lz4_launch_count(void);
+
+/* Decoder path counters of `device` since the last reset: out4[0] blocks decoded by the
+ * shared-memory tile kernel (two CTAs per SM), [1] by its big-stage variant, [2] by the exact
+ * warp-per-block decoder (malformed / oversized / unusual blocks), [3] parse repair walks.
+ * Synchronises the device.  Diagnostics only (tests assert that clean data stays on the tile path). */
+K4LZ4_API int32_t k4lz4_decode_stats(int32_t device, uint64_t *out4, int32_t reset);
 
 #ifdef __cplusplus
 }

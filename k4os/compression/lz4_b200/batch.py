@@ -13,6 +13,8 @@ from typing import Sequence
 
 import numpy as np
 
+import ctypes as C
+
 from . import _native as N
 
 
@@ -104,6 +106,25 @@ def pickle_batch_host(messages: Sequence, level: int = 0, device: int = 0):
     N.check(N.lib().k4lz4_pickle_batch(src.ctypes.data, so.ctypes.data, sl.ctypes.data,
                                        dst.ctypes.data, do.ctypes.data, out.ctypes.data,
                                        n, int(level), N.MEM_HOST, None, int(device)))
+    res = [dst[do[i]:do[i] + out[i]].tobytes() if out[i] > 0 else b"" for i in range(n)]
+    return res, out
+
+
+def pickle_writer_batch_host(messages: Sequence, level: int = 0, device: int = 0):
+    """LZ4Pickler.Pickle<TBufferWriter> over a batch -> (list[bytes], outLen int32[n]): what the
+    reference would have advanced each writer by (LZ4Pickler.pickle.cs:113-148)."""
+    src, so, sl = _pack(messages)
+    n = len(sl)
+    L = N.lib()
+    bound = np.array([L.k4lz4_pickle_writer_bound(int(v)) for v in sl], dtype=np.int64)
+    do = np.zeros(n, dtype=np.int64)
+    if n:
+        do[1:] = np.cumsum(bound[:-1])
+    dst = np.full(int(bound.sum()) + 1, 0xCD, dtype=np.uint8)
+    out = np.full(n, -1, dtype=np.int32)
+    N.check(L.k4lz4_pickle_writer_batch(src.ctypes.data, so.ctypes.data, sl.ctypes.data,
+                                        dst.ctypes.data, do.ctypes.data, out.ctypes.data,
+                                        n, int(level), N.MEM_HOST, None, int(device)))
     res = [dst[do[i]:do[i] + out[i]].tobytes() if out[i] > 0 else b"" for i in range(n)]
     return res, out
 
@@ -205,3 +226,44 @@ def copy_blocks_device(src_ptr: int, src_off_ptr: int, dst_ptr: int, dst_off_ptr
                        n: int, stream: int = 0, device: int = -1) -> None:
     N.check(N.lib().k4lz4_copy_blocks_device(src_ptr, src_off_ptr, dst_ptr, dst_off_ptr, len_ptr,
                                              int(n), stream or None, int(device)))
+
+
+def decode_stats(device: int = 0, reset: bool = False) -> dict:
+    """Decoder path counters (k4lz4_decode_stats): which engine decoded how many blocks."""
+    v = (C.c_uint64 * 4)()
+    N.check(N.lib().k4lz4_decode_stats(device, C.addressof(v), int(reset)))
+    return {"tile": int(v[0]), "tile_big": int(v[1]), "generic": int(v[2]), "repair_walks": int(v[3])}
+
+
+def decode_dict_batch_host(blocks: Sequence, caps: Sequence[int], dicts: Sequence, device: int = 0):
+    """LZ4Codec.Decode(source, target, dictionary) over a batch (k4lz4_decode_dict_batch, host memory).
+    Returns (list of bytes, int32 results)."""
+    src, so, sl = _pack(blocks)
+    dic, do, dl = _pack(dicts)
+    n = len(sl)
+    caps = _i32(caps)
+    doff = np.zeros(n, dtype=np.int64)
+    if n > 1:
+        doff[1:] = np.cumsum(np.maximum(caps[:-1], 0).astype(np.int64))
+    dst = np.zeros(int(np.maximum(caps, 0).sum()) + 16, dtype=np.uint8)
+    out = np.zeros(n, dtype=np.int32)
+    N.check(N.lib().k4lz4_decode_dict_batch(src.ctypes.data, so.ctypes.data, sl.ctypes.data, dst.ctypes.data,
+                                            doff.ctypes.data, caps.ctypes.data, dic.ctypes.data, do.ctypes.data,
+                                            dl.ctypes.data, out.ctypes.data, n, N.MEM_HOST, None, int(device)))
+    return [dst[doff[i]:doff[i] + max(int(out[i]), 0)].tobytes() for i in range(n)], out
+
+
+def partial_decode_batch_host(blocks: Sequence, targets: Sequence[int], device: int = 0):
+    """LZ4Codec.PartialDecode over a batch (k4lz4_partial_decode_batch, host memory)."""
+    src, so, sl = _pack(blocks)
+    n = len(sl)
+    tg = _i32(targets)
+    doff = np.zeros(n, dtype=np.int64)
+    if n > 1:
+        doff[1:] = np.cumsum(np.maximum(tg[:-1], 0).astype(np.int64))
+    dst = np.zeros(int(np.maximum(tg, 0).sum()) + 16, dtype=np.uint8)
+    out = np.zeros(n, dtype=np.int32)
+    N.check(N.lib().k4lz4_partial_decode_batch(src.ctypes.data, so.ctypes.data, sl.ctypes.data, dst.ctypes.data,
+                                               doff.ctypes.data, tg.ctypes.data, out.ctypes.data, n,
+                                               N.MEM_HOST, None, int(device)))
+    return [dst[doff[i]:doff[i] + max(int(out[i]), 0)].tobytes() for i in range(n)], out

@@ -108,10 +108,43 @@ class LZ4Codec:
     # -- Decode ---------------------------------------------------------------------------
     @staticmethod
     def Decode(source, *args) -> int:
-        """Decode(source, target)                                          -- LZ4Codec.cs:179-191
+        """Decode(source, target[, dictionary])                            -- LZ4Codec.cs:179-191, :200-214
         Decode(source, sourceOffset, sourceLength, target, targetOffset, targetLength)
                                                                           -- LZ4Codec.cs:225-237
         Returns bytes written, 0 for empty input, negative on malformed input / small target."""
+        dic = None
+        if len(args) >= 5:
+            s_off, s_len, target, t_off, t_len = args[:5]
+            _validate(source, s_off, s_len, "source")
+            _validate(target, t_off, t_len, "target")
+            src = _ro(source)[s_off:s_off + s_len]
+            dst = _rw(target)[t_off:t_off + t_len]
+            if len(args) >= 8:                                            # ..., dictionary, dictOffset, dictLength
+                dictionary, d_off, d_len = args[5:8]
+                if dictionary is not None or d_len:
+                    _validate(dictionary, d_off, d_len, "dictionary")
+                    dic = _ro(dictionary)[d_off:d_off + d_len]
+        else:
+            src, dst = _ro(source), _rw(args[0])
+            if len(args) >= 2 and args[1] is not None:                    # Decode(source, target, dictionary)
+                dic = _ro(args[1])
+        n = int(src.shape[0])
+        if n <= 0:
+            return 0
+        if dic is not None and int(dic.shape[0]) > 0:                     # LZ4Codec.cs:144-157, :200-214, :246-265
+            r = int(N.lib().k4lz4_decode_dict(src.ctypes.data, n, dst.ctypes.data, int(dst.shape[0]),
+                                              dic.ctypes.data, int(dic.shape[0])))
+        else:
+            r = int(N.lib().k4lz4_decode(src.ctypes.data, n, dst.ctypes.data, int(dst.shape[0])))
+        if r <= N.E_NODEVICE:
+            N.check(r)
+        return r
+
+    @staticmethod
+    def PartialDecode(source, *args) -> int:
+        """PartialDecode(source, target)                                   -- LZ4Codec.cs:163-173
+        PartialDecode(source, sourceOffset, sourceLength, target, targetOffset, targetLength)
+        Decoding stops at the end of the target; returns bytes written, negative on failure."""
         if len(args) >= 5:
             s_off, s_len, target, t_off, t_len = args[:5]
             _validate(source, s_off, s_len, "source")
@@ -123,7 +156,7 @@ class LZ4Codec:
         n = int(src.shape[0])
         if n <= 0:
             return 0
-        r = int(N.lib().k4lz4_decode(src.ctypes.data, n, dst.ctypes.data, int(dst.shape[0])))
+        r = int(N.lib().k4lz4_partial_decode(src.ctypes.data, n, dst.ctypes.data, int(dst.shape[0])))
         if r <= N.E_NODEVICE:
             N.check(r)
         return r

@@ -99,6 +99,117 @@ __device__ int decode_block_warp(const uint8_t* __restrict__ src, int n,
     }
 }
 
+// LZ77 copy through the virtual window [dict | dst]: byte i of the match comes from window position
+// match + (i mod offset), which lies in [op - offset, op) -- final bytes of the dictionary (negative
+// positions) or of the block; no lane depends on another lane of the same copy.
+__device__ __forceinline__ void warp_copy_match_window(uint8_t* dst, int64_t op, int64_t match, int len, int offset,
+                                                       const uint8_t* __restrict__ dict, int dictSize, int lane) {
+    __syncwarp();
+    if (offset == 0) { for (int i = lane; i < len; i += 32) dst[op + i] = 0; return; }
+    for (int i = lane; i < len; i += 32) {
+        const int64_t j = match + (offset >= len ? i : i % offset);
+        dst[op + i] = j < 0 ? __ldg(dict + dictSize + j) : dst[j];
+    }
+}
+
+// The general form of decode_block_warp: external dictionary (LZ4_decompress_safe_usingDict,
+// LL64.dec.cs:523-546 -> forceExtDict :510-521; the prefix variants read the same bytes and reject
+// the same offsets) and/or partial decoding (LZ4_decompress_safe_partial :548-556 with
+// dstCapacity == targetOutputSize, LLxx.cs:29-39; paths :256-280, :301-307, :387-406).
+__device__ int decode_block_warp_general(const uint8_t* __restrict__ src, int n, uint8_t* __restrict__ dst,
+                                         int outputSize, bool partial,
+                                         const uint8_t* __restrict__ dict, int dictSize) {
+    const int lane = lane_id();
+    int64_t ip = 0, op = 0;
+    const int64_t iend = n, oend = outputSize;
+    const int64_t shortiend = iend - 16, shortoend = oend - 32;
+    const bool checkOffset = dictSize < 65536;                       // :147
+    const bool extDict = dict != nullptr && dictSize > 0;
+    if (!extDict) dictSize = 0;
+
+    if (outputSize == 0) {                                           // :162-168
+        if (partial) return 0;
+        return (n == 1 && __ldg(src) == 0) ? 0 : -1;
+    }
+    if (n == 0) return -1;
+
+    for (;;) {
+        const uint32_t token = __ldg(src + ip); ip++;
+        int64_t len = token >> 4;
+        const bool shortcut = (len != 15) && (ip < shortiend) && (op <= shortoend);
+        bool literalsDone = false;
+        if (!shortcut) {
+            if (len == 15) {
+                if (ip >= iend - 15) return -1;
+                for (;;) {
+                    uint32_t s = __ldg(src + ip); ip++;
+                    len += s;
+                    if (ip >= iend - 15) break;
+                    if (s != 255) break;
+                }
+            }
+            int64_t cpy = op + len;
+            if (cpy > oend - MFLIMIT || ip + len > iend - (2 + 1 + LASTLITERALS)) {
+                if (partial) {                                       // :256-280
+                    if (ip + len > iend - (2 + 1 + LASTLITERALS) && ip + len != iend) return -1;
+                    if (cpy > oend) { cpy = oend; len = oend - op; }
+                } else if (ip + len != iend || cpy > oend) return -1;   // :291-294
+                warp_copy_in(dst + op, src + ip, (int)len, lane);
+                ip += len; op += len;
+                if (!partial || cpy == oend || ip == iend) return (int)op;   // :304-307
+                literalsDone = true;
+            }
+        }
+        if (!literalsDone) {
+            warp_copy_in(dst + op, src + ip, (int)len, lane);
+            ip += len; op += len;
+        }
+
+        const int offset = (int)__ldg(src + ip) | ((int)__ldg(src + ip + 1) << 8);
+        ip += 2;
+        const int64_t match = op - offset;
+        len = token & 15;
+
+        if (shortcut && len != 15 && offset >= 8 && match >= 0) {    // :211-220 (match >= lowPrefix == dst)
+            len += MINMATCH;
+            warp_copy_match(dst, op, match, (int)len, offset, lane);
+            op += len;
+            continue;
+        }
+        if (len == 15) {
+            for (;;) {
+                uint32_t s = __ldg(src + ip); ip++;
+                len += s;
+                if (ip >= iend - LASTLITERALS + 1) return -1;
+                if (s != 255) break;
+            }
+        }
+        len += MINMATCH;
+        if (checkOffset && match + dictSize < 0) return -1;          // :338
+        if (match < 0) {
+            if (!extDict) return -1;                                  // (unreachable with checkOffset on)
+            if (op + len > oend - LASTLITERALS) {                     // :343-347
+                if (partial) len = (oend - op) < len ? (oend - op) : len;
+                else return -1;
+            }
+            warp_copy_match_window(dst, op, match, (int)len, offset, dict, dictSize, lane);
+            op += len;
+            continue;
+        }
+        const int64_t cpy = op + len;
+        if (partial && cpy > oend - 12) {                            // :387-406
+            const int64_t mlen = len < oend - op ? len : oend - op;
+            warp_copy_match(dst, op, match, (int)mlen, offset, lane);
+            op += mlen;
+            if (op == oend) return (int)op;
+            continue;
+        }
+        if (cpy > oend - LASTLITERALS) return -1;                    // :427-433
+        warp_copy_match(dst, op, match, (int)len, offset, lane);
+        op = cpy;
+    }
+}
+
 // LZ4Codec.Decode post-processing (LZ4Codec.cs:104-115): len <= 0 -> 0 ; result <= 0 -> -1.
 __device__ __forceinline__ int codec_decode_warp(const uint8_t* src, int n, uint8_t* dst, int cap) {
     if (n <= 0) return 0;
@@ -117,6 +228,30 @@ decode_generic_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __rest
     const int b = workList ? workList[w] : w;
     if (b < 0 || b >= nBlocks) return;
     int r = codec_decode_warp(srcBase + srcOff[b], srcLen[b], dstBase + dstOff[b], dstCap[b]);
+    if (lane_id() == 0) outLen[b] = r;
+}
+
+// LZ4Codec.Decode(src, dst, dict) / LZ4Codec.PartialDecode over a batch: warp per block.
+// dictOff/dictLen may be null (no dictionaries); partial != 0 selects PartialDecode semantics
+// (dstCap[i] is then the target length).
+__global__ void __launch_bounds__(128)
+decode_general_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restrict__ srcOff,
+                      const int32_t* __restrict__ srcLen, uint8_t* __restrict__ dstBase,
+                      const int64_t* __restrict__ dstOff, const int32_t* __restrict__ dstCap,
+                      const uint8_t* __restrict__ dictBase, const int64_t* __restrict__ dictOff,
+                      const int32_t* __restrict__ dictLen, int32_t* __restrict__ outLen, int nBlocks,
+                      int partial) {
+    const int b = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (b >= nBlocks) return;
+    const int n = srcLen[b];
+    int r;
+    if (n <= 0) r = 0;                                               // LZ4Codec.cs:129-130, 150-151
+    else {
+        const int dl = (dictBase && dictLen) ? dictLen[b] : 0;
+        r = decode_block_warp_general(srcBase + srcOff[b], n, dstBase + dstOff[b], dstCap[b] < 0 ? 0 : dstCap[b],
+                                      partial != 0, dl > 0 ? dictBase + dictOff[b] : nullptr, dl > 0 ? dl : 0);
+        r = r <= 0 ? -1 : r;
+    }
     if (lane_id() == 0) outLen[b] = r;
 }
 

@@ -1,62 +1,117 @@
-// decode_tile.cuh -- pass 2 of the batched LZ4 block decoder for B200, and the launch policy.
+// decode_tile.cuh -- the batched LZ4 block decoder for B200: ONE kernel, ONE CTA per block.
 //
-//   pass 1  decode_parse.cuh   thread per block: validated sequence descriptors
-//   pass 2  decode_copy_kernel one CTA (384 threads) per block.  The compressed block is pulled
-//           into shared memory with TMA bulk copies (cp.async.bulk global -> shared, 8 KiB pieces,
-//           one mbarrier each) and the 64 KiB output tile is built in shared memory as well, so
-//           every byte the copy loop touches is a shared-memory access.  Warps take batches of
-//           32 consecutive sequences, ONE SEQUENCE PER LANE: lane-parallel literal copies, then
-//           lane-parallel match copies under EXACT BYTE-LEVEL dependencies: a bitmap with one bit
-//           per output byte (8 KiB) records which bytes are final; a writer ORs its byte mask in
-//           after a block-scope fence, a match is copied as soon as the bits of the bytes it reads
-//           are set.  (Measured alternatives: per-batch done flags 38 ms, per-sequence flags through
-//           a granule map 21 ms, this bitmap 13 ms per 4 GiB.)  Long runs are copied by the whole
-//           warp.  The finished tile leaves through one TMA bulk store (cp.async.bulk shared -> global).
+// A CTA (512 threads) owns one block.  Everything a block needs lives in shared memory: the
+// compressed stream (pulled in by one TMA bulk copy), the 64 KiB output tile (left through one
+// TMA bulk store) and a few KiB of bookkeeping; the compressed stream is read from HBM once, the
+// raw block is written once, nothing else moves.
 //
-// Two instantiations: STAGE = 40 KiB (two CTAs per SM: 64 + 40 + 8 KiB; blocks whose compressed
-// size fits) and STAGE = 66 KiB (one CTA per SM; everything else that still fits the 64 KiB tile).
-// Blocks that do not fit the tile at all (decoded size > 64 KiB) go to the warp-per-block generic
-// decoder inside the same launch.
+//   1. SEGMENTED SPECULATIVE PARSE.  The token chain is the only serial part of LZ4 decoding.
+//      The stream is cut into 256-byte segments, one lane each.  A lane starts walking 384 bytes
+//      BEFORE its segment at an arbitrary byte (LZ4 chains are confluent: a walk started anywhere
+//      falls onto the true chain within a few sequences), notes the first position it reaches
+//      inside its segment (entry) and the first one past it (exit), and counts the sequences and
+//      output bytes in between.  Lane 0 is exact; lane t is right iff entry[t] == exit[t-1];
+//      wrong lanes re-walk from exit[t-1] until every link agrees (typically 0-1 rounds).
+//   2. BLOCK-WIDE EXCLUSIVE SCAN of the per-segment sequence counts and output sizes gives every
+//      segment its first sequence index and output position; a second walk writes one 32-bit
+//      descriptor (tokenPos | outPos << 16) per sequence into the still unused TAIL of the output
+//      tile.  (A sequence produces >= 4 output bytes and its descriptor is 4 bytes, so the output
+//      front never overtakes the descriptors of sequences that have not been decoded yet.)
+//   3. STEPS of 512 consecutive sequences, one per thread: literals and every match whose source
+//      lies entirely before the step's first output byte ("far") are copied at once, lane-parallel
+//      for short runs, by the whole warp in 4-byte words for long ones.  The remaining "near"
+//      matches (source reaches into the step's own output) are compacted into a sorted interval
+//      list; a near match is copied as soon as no still-pending interval intersects its source
+//      (binary search once, then a flag scan per round); rounds are separated by CTA barriers,
+//      chains inside one warp resolve without a barrier.
+//
+// The fast path accepts a block only when every sequence satisfies the reference decoder's
+// accept tests with room to spare (so the shortcut and the general path of the reference agree);
+// anything else -- malformed input, decoded size > 64 KiB or > dstCap, offset 0, > 16384
+// sequences, compressed size > 65535 -- is handed UNTOUCHED to the exact warp-per-block decoder
+// (decode_generic.cuh), which reproduces LL64.dec.cs test by test.  Nothing reaches global memory
+// before a block is known to be clean.
 //
 // Reference semantics: /root/reference/src/K4os.Compression.LZ4/Engine/x64/LL64.dec.cs:124-477,
 // Engine/LL.tools.cs:165-193 (LZ4_readVLE), LZ4Codec.cs:104-115.
 #pragma once
-#include <cstdlib>
+#include <mutex>
+
 #include "common.cuh"
 #include "decode_generic.cuh"
-#include "decode_parse.cuh"
 
 namespace k4 {
 
-constexpr int SUB_BATCH = 65536;         // blocks per parse/copy kernel pair
-#ifndef K4_COPY_THREADS
-#define K4_COPY_THREADS 384
+constexpr int TILE_BYTES = 65536;
+constexpr int TILE_PAD = 32;             // slack behind the tile: output shift (<= 15) + descriptor safety
+#ifndef K4_DT_THREADS
+#define K4_DT_THREADS 512
 #endif
-constexpr int COPY_THREADS = K4_COPY_THREADS;
-constexpr int COPY_WARPS = COPY_THREADS / 32;
-constexpr int STAGE_PIECE = 8192;        // bytes per TMA bulk load / mbarrier
-constexpr int STAGE_SMALL = 40 * 1024;   // compressed bytes (incl. alignment slack) staged, 2 CTAs/SM
-constexpr int STAGE_BIG = 66 * 1024;     // ... 1 CTA/SM; covers LZ4_compressBound(65536) + slack
-constexpr int MAX_PIECES = (STAGE_BIG + STAGE_PIECE - 1) / STAGE_PIECE;   // 9
+constexpr int DT_THREADS = K4_DT_THREADS;
+constexpr int DT_WARPS = DT_THREADS / 32;
+constexpr int DT_K = DT_THREADS;         // sequences per step
+#ifndef K4_DT_SEG
+#define K4_DT_SEG 128
+#endif
+#ifndef K4_DT_WARM
+#define K4_DT_WARM 256
+#endif
+constexpr int DT_SEG = K4_DT_SEG;        // compressed bytes per parse lane
+constexpr int DT_WARM = K4_DT_WARM;      // speculative warm-up before the segment
+#ifndef K4_DT_HUGE
+#define K4_DT_HUGE 512
+#endif
+constexpr int DT_HUGE = K4_DT_HUGE;      // runs of at least this many bytes are copied word-wise by the whole warp
+constexpr int STAGE_SMALL = 40 * 1024;   // two CTAs per SM
+constexpr int STAGE_BIG = 65536 + 32;    // one CTA per SM: every block the tile path can take
+constexpr int DT_NMAX = 16384;           // sequences per block the tile tail can describe
+constexpr int DT_MAX_SRC = 65535;        // token positions are 16-bit
+constexpr uint32_t DT_NONE = 0xFFFFFFFFu;
+constexpr int SQ_LAST = 1, SQ_BAD = 2;
+
+// counters (per device): [0] blocks decoded by the small-stage tile path, [1] by the big-stage
+// tile path, [2] by the exact generic decoder, [3] parse repair walks
+__device__ unsigned long long g_decode_stats[4];
+
+// -DK4_DT_PROFILE (tools only, never the shipped build): per-phase cycle sums of thread 0 of every CTA
+#ifdef K4_DT_PROFILE
+__device__ unsigned long long g_decode_prof[32];
+#define DT_PROF_DECL long long pfT = clock64();
+#define DT_PROF(slot) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_decode_prof[slot], (unsigned long long)(t_ - pfT)); pfT = t_; } } while (0)
+#define DT_PROF_COUNT(slot, v) do { if (threadIdx.x == 0) atomicAdd(&g_decode_prof[slot], (unsigned long long)(v)); } while (0)
+#else
+#define DT_PROF_DECL
+#define DT_PROF(slot) do {} while (0)
+#define DT_PROF_COUNT(slot, v) do {} while (0)
+#endif
 
 template <int STAGE>
-struct CopySmem {
-    uint8_t tile[TILE_BYTES];
-    uint8_t stage[STAGE];
-    volatile uint32_t ready[TILE_BYTES / 32];  // one bit per output byte: the byte is final in the tile
-    unsigned long long bar[MAX_PIECES];        // one mbarrier per staged piece
+struct TileSmem {
+    static constexpr int MAXSEG = (STAGE + DT_SEG - 1) / DT_SEG + 1;
+    alignas(128) uint8_t tile[TILE_BYTES + TILE_PAD];
+    alignas(16) uint8_t stage[STAGE];
+    uint32_t segOut[MAXSEG];             // output bytes of the sequences starting in the segment
+    uint16_t segEntry[MAXSEG];           // first chain position >= segment start
+    uint16_t segExit[MAXSEG];            // first chain position >= segment end
+    uint16_t segN[MAXSEG];               // sequences starting in the segment | bad << 15
+    uint32_t nearIv[DT_K];               // destFirst | destLast << 16, sorted
+    uint16_t nearOff[DT_K];              // match distance of the entry
+    uint8_t nearFlag[DT_K];              // 1 = still pending
+    uint32_t warpA[DT_WARPS];
+    uint32_t warpB[DT_WARPS];
+    uint32_t nearCnt[2][DT_WARPS];       // per-warp near-match counts, double-buffered by step parity
+    alignas(8) unsigned long long bar;
 };
 
-__device__ __forceinline__ void tma_store_tile(uint8_t* gdst, const uint8_t* stile, int bytes) {
-    // generic-proxy writes -> async proxy, then one bulk copy shared::cta -> global
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(stile);
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 :: "l"(gdst), "r"(saddr), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
+static_assert(sizeof(TileSmem<STAGE_SMALL>) <= 115712, "two CTAs per SM: (228 KiB - 2 x 1 KiB) / 2");
+static_assert(sizeof(TileSmem<STAGE_BIG>) <= 232448, "one CTA per SM: 227 KiB");
 
+// ---- small PTX helpers ----------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(a), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
     uint32_t ok;
@@ -65,356 +120,620 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
                      "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
     } while (!ok);
 }
+// global -> shared bulk copy (TMA), completion on an mbarrier; all three of dst/src/bytes 16-aligned
+__device__ __forceinline__ void tma_load(void* sdst, const void* gsrc, int bytes, unsigned long long* bar) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(sdst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(a), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(d), "l"(gsrc), "r"(bytes), "r"(a) : "memory");
+}
+// shared -> global bulk copy (TMA); returns when the shared source has been read
+__device__ __forceinline__ void tma_store(void* gdst, const void* ssrc, int bytes) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(s), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// WAITMODE: 1 = poll with nanosleep back-off (product); 2 = no waiting (timing experiments only: wrong output)
-template <int STAGE, int WAITMODE>
-__global__ void __launch_bounds__(COPY_THREADS, (COPY_THREADS <= 512 ? 2 : 1))
-decode_copy_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restrict__ srcOff,
-                   const int32_t* __restrict__ srcLen, uint8_t* __restrict__ dstBase,
-                   const int64_t* __restrict__ dstOff, const int32_t* __restrict__ dstCap,
-                   int32_t* __restrict__ outLen, const BlockInfo* __restrict__ info,
-                   const uint32_t* __restrict__ descs, int first) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    CopySmem<STAGE>& S = *reinterpret_cast<CopySmem<STAGE>*>(smem_raw);
-    const int t = blockIdx.x;
-    const int b = first + t;
-    const BlockInfo bi = info[t];
-    const int lane = threadIdx.x & 31;
-    // the hardware arbiter favours high warp ids: give them the EARLIEST batches, the ones every
-    // other warp may be waiting for
-    const int warp = COPY_WARPS - 1 - (int)(threadIdx.x >> 5);
+// ---- sequence header ------------------------------------------------------------------------
+// Header of the sequence whose token sits at stream position p (stage4 = the stage as aligned
+// words, stg[x] = stream byte x, sx = shift): two unaligned 4-byte windows -- token + first
+// length byte, offset + first match-length byte -- decode the common case without a branch; only
+// 255-chains take the byte loop.  ml includes MINMATCH and is 0 for the terminal (literal-only)
+// sequence.  flags: SQ_LAST terminal, SQ_BAD the stream cannot be a clean block, SQ_EDGE (EXACT
+// only) one of the reference's length-overrun tests would fire (LL.tools.cs:165-193,
+// LL64.dec.cs:231-232,329-331).  Every access stays below stream position n + 8.
+constexpr int SQ_EDGE = 4;
+__device__ __forceinline__ uint32_t stage_load4(const uint32_t* stage4, const int x) {
+    const uint32_t w0 = stage4[x >> 2], w1 = stage4[(x >> 2) + 1];
+    return __funnelshift_r(w0, w1, (x & 3) * 8);
+}
+template <bool EXACT>
+__device__ __forceinline__ void seq_header(const uint32_t* stage4, const uint8_t* stg, const int sx,
+                                           const int p, const int n, int& lit, int& litPos, int& ml,
+                                           int& off, int& next, uint32_t& flags) {
+    const uint32_t w = stage_load4(stage4, sx + p);
+    const uint32_t tok = w & 0xFFu;
+    int q = p + 1;
+    lit = (int)(tok >> 4);
+    flags = 0;
+    if (lit == 15) {
+        const uint32_t e1 = (w >> 8) & 0xFFu;
+        if (EXACT && q >= n - 15) flags |= SQ_EDGE;            // initial overrun
+        lit += (int)e1; q++;
+        if (e1 == 255u) {                                       // rare: >= 270 literals
+            if (EXACT && q >= n - 15) flags |= SQ_EDGE;
+            while (q < n) {
+                const uint32_t s = stg[q]; q++; lit += (int)s;
+                if (s != 255u) break;
+                if (EXACT && q >= n - 15) flags |= SQ_EDGE;    // the reference stops early here
+            }
+        }
+    }
+    litPos = q;
+    const int litEnd = q + lit;
+    if (litEnd + 2 > n) {                                       // no room for an offset: terminal sequence
+        next = n; ml = 0; off = 0;
+        flags |= SQ_LAST | (litEnd != n ? SQ_BAD : 0);
+        return;
+    }
+    const uint32_t w2 = stage_load4(stage4, sx + litEnd);
+    off = (int)(w2 & 0xFFFFu);
+    ml = (int)(tok & 15u);
+    q = litEnd + 2;
+    if (ml == 15) {
+        const uint32_t m1 = (w2 >> 16) & 0xFFu;
+        ml += (int)m1; q++;
+        if (EXACT && q >= n - 4) flags |= SQ_EDGE;             // any overrun is fatal in the reference
+        if (m1 == 255u) {
+            while (q < n) {
+                const uint32_t s = stg[q]; q++; ml += (int)s;
+                if (EXACT && q >= n - 4) flags |= SQ_EDGE;
+                if (s != 255u) break;
+            }
+        }
+    }
+    ml += MINMATCH;
+    if (q >= n) flags |= SQ_BAD;                                // a block never ends with a match
+    next = q < n ? q : n;
+}
 
-    if (bi.status == ST_DONE) return;
-    const uint8_t* __restrict__ src = srcBase + srcOff[b];
-    const int n = srcLen[b];
-    const int shift = (int)(reinterpret_cast<uintptr_t>(src) & 15);
-    const int staged = (n + shift + 15) & ~15;           // bytes pulled in, from the aligned base
-    const bool big = staged > STAGE_SMALL;
-    if (bi.status == ST_FALLBACK || staged > STAGE_BIG) {
-        if (STAGE != STAGE_SMALL) return;                // handled once, by the small-stage launch
-        if (warp == 0) {
-            const int r = codec_decode_warp(src, n, dstBase + dstOff[b], dstCap[b]);
-            if (lane == 0) outLen[b] = r;
+// ---- copies inside shared memory ------------------------------------------------------------
+// whole warp, uniform arguments, source and destination do not overlap: destination-aligned
+// 4-byte words built from two aligned source words
+__device__ __forceinline__ void warp_copy(uint8_t* d, const uint8_t* s, int len, const int lane) {
+    const int h0 = (int)((4u - ((uint32_t)(uintptr_t)d & 3u)) & 3u);
+    const int h = h0 < len ? h0 : len;
+    if (lane < h) d[lane] = s[lane];
+    d += h; s += h; len -= h;
+    const int nw = len >> 2;
+    const uint32_t sh = ((uint32_t)(uintptr_t)s & 3u) * 8u;
+    const uint32_t* s4 = reinterpret_cast<const uint32_t*>(s - (sh >> 3));
+    uint32_t* d4 = reinterpret_cast<uint32_t*>(d);
+    for (int w = lane; w < nw; w += 32) {
+        const uint32_t lo = s4[w];
+        const uint32_t hi = sh ? s4[w + 1] : 0u;
+        d4[w] = __funnelshift_r(lo, hi, sh);
+    }
+    const int t = len & 3;
+    if (lane < t) d[4 * nw + lane] = s[4 * nw + lane];
+}
+// whole warp, LZ77 match of `len` bytes at d with distance off (uniform arguments)
+__device__ __forceinline__ void warp_copy_match_smem(uint8_t* d, const int off, const int len, const int lane) {
+    if (off >= len) { warp_copy(d, d - off, len, lane); return; }
+    if (off >= 160) {
+        // overlapping but far enough apart: 128-byte slices, each one reads only bytes that earlier
+        // slices (or the time before the copy) made final
+        for (int i = 0; i < len; i += 128) {
+            const int c = len - i < 128 ? len - i : 128;
+            warp_copy(d + i, d + i - off, c, lane);
+            __syncwarp();
         }
         return;
     }
-    if (big != (STAGE == STAGE_BIG)) return;             // the other instantiation owns this block
+    const uint8_t* s = d - off;                 // periodic: every byte comes from the final window [d-off, d)
+    for (int i = lane; i < len; i += 32) d[i] = s[i % off];
+}
 
-    const uint32_t* __restrict__ d = descs + (size_t)t * DESC_CAP;
-    const int nseq = bi.nseq;
-    const int nbatch = (nseq + 31) >> 5;
-    uint8_t* tile = S.tile;
-    const uint8_t* stg = S.stage + shift;                // stg[p] == src[p]
-    const int npieces = (staged + STAGE_PIECE - 1) / STAGE_PIECE;
+// Balanced copy of many short runs by one warp.  Lane i owns an item made of c_i pieces of up to
+// DT_PIECE bytes; the pieces of all 32 items are numbered consecutively and handed out 32 at a
+// time, one per lane, so the work per lane is even no matter how the run lengths are distributed.
+// Owner lookup without shared memory: the non-empty lanes set a bit at their first piece number
+// (one warp OR-reduction per pass), a lane finds the rank of its piece's owner with a popcount and
+// the owner's lane through a rank -> lane table held in registers.  body(ownerLane, j, live) is
+// called by ALL lanes (it may shuffle); j = index of the piece inside the owner's item.
+#ifndef K4_DT_PIECE
+#define K4_DT_PIECE 8
+#endif
+constexpr int DT_PIECE = K4_DT_PIECE;
+template <class Body>
+__device__ __forceinline__ void warp_expand(const int c, const int lane, Body&& body) {
+    int incl = c;
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, dlt);
+        if (lane >= dlt) incl += v;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    if (total == 0) return;
+    const int s = incl - c;                                      // first piece number of my item
+    const unsigned nz = __ballot_sync(FULL, c > 0);
+    const int rankToLane = (int)__fns(nz, 0, lane + 1);          // lane of the (lane+1)-th non-empty item
+    for (int base = 0; base < total; base += 32) {
+        const bool startsHere = c > 0 && s >= base && s < base + 32;
+        const unsigned M = __reduce_or_sync(FULL, startsHere ? 1u << (s - base) : 0u);
+        const int baseRank = __popc(__ballot_sync(FULL, c > 0 && s < base)) - 1;
+        const int g = base + lane;
+        const int ownerRank = baseRank + __popc(M & (0xFFFFFFFFu >> (31 - lane)));
+        const int ownerLane = __shfl_sync(FULL, rankToLane, ownerRank & 31);
+        const int sOwner = __shfl_sync(FULL, s, ownerLane & 31);
+        body(ownerLane & 31, g - sOwner, g < total);
+    }
+}
+// one piece: up to DT_PIECE bytes, all loads before all stores
+__device__ __forceinline__ void piece_copy(uint8_t* dst, const uint8_t* src, const int len) {
+    uint8_t v[DT_PIECE];
+#pragma unroll
+    for (int j = 0; j < DT_PIECE; j++) if (j < len) v[j] = src[j];
+#pragma unroll
+    for (int j = 0; j < DT_PIECE; j++) if (j < len) dst[j] = v[j];
+}
 
-    // ---- prologue: TMA loads of the compressed block, done flags, granule -> batch map ---------
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < npieces; i++) {
-            const uint32_t a = (uint32_t)__cvta_generic_to_shared(&S.bar[i]);
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(a) : "memory");
+// ---- the tile decoder ---------------------------------------------------------------------------
+// All DT_THREADS threads of the CTA call it with the same arguments.  Requires 1 <= n <= DT_MAX_SRC,
+// (src & 15) + n + 16 <= STAGE, cap >= 1.  Returns the decoded size (> 0) after the bytes have been
+// written to gdst, or -1 -- nothing written -- when the block has to go to the exact decoder.
+template <int STAGE>
+__device__ int tile_decode_block(TileSmem<STAGE>& S, const uint8_t* __restrict__ src, const int n,
+                                 uint8_t* __restrict__ gdst, const int cap, uint32_t& barParity) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int shift = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+    uint8_t* const stg = S.stage + shift;                       // stg[p] == src[p]
+    const uint32_t* const stage4 = reinterpret_cast<const uint32_t*>(S.stage);
+    DT_PROF_DECL
+
+    // ---- compressed block -> shared memory: aligned middle by TMA, ragged ends by plain loads ----
+    {
+        const int headRaw = (16 - shift) & 15;
+        const int head = headRaw < n ? headRaw : n;
+        const int mid = (n - head) & ~15;
+        const int tail = n - head - mid;
+        if (tid == 0 && mid > 0) {
+            fence_async_smem();
+            tma_load(stg + head, src + head, mid, &S.bar);
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint8_t* gsrc = src - shift;
-        for (int i = 0; i < npieces; i++) {
-            const int off = i * STAGE_PIECE;
-            const int bytes = (staged - off) < STAGE_PIECE ? (staged - off) : STAGE_PIECE;
-            const uint32_t a = (uint32_t)__cvta_generic_to_shared(&S.bar[i]);
-            const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(S.stage + off);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(a), "r"(bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         :: "r"(sdst), "l"(gsrc + off), "r"(bytes), "r"(a) : "memory");
+        if (tid >= 32 && tid < 32 + head) stg[tid - 32] = src[tid - 32];
+        if (tid >= 64 && tid < 64 + tail) stg[head + mid + tid - 64] = src[head + mid + tid - 64];
+        if (mid > 0) { mbar_wait(&S.bar, barParity); barParity ^= 1u; }
+    }
+    __syncthreads();
+    DT_PROF(0);
+
+    // ---- 1. segmented speculative parse ------------------------------------------------------------
+    const int NS = (n + DT_SEG - 1) / DT_SEG;
+    const int segStart = tid * DT_SEG;
+    const int segEnd = segStart + DT_SEG < n ? segStart + DT_SEG : n;
+    // walks from p to the end of the lane's segment; counts what starts inside the segment
+    auto walk = [&](int p) {
+        uint32_t entry = 0xFFFFFFFFu, cnt = 0, ob = 0, bad = 0;
+        while (p < segEnd) {
+            int lit, litPos, ml, off, nx; uint32_t fl;
+            seq_header<false>(stage4, stg, shift, p, n, lit, litPos, ml, off, nx, fl);
+            if (p >= segStart) {
+                entry = entry < (uint32_t)p ? entry : (uint32_t)p;
+                cnt++; ob += (uint32_t)(lit + ml); bad |= fl & SQ_BAD;
+            }
+            p = nx;
+        }
+        S.segEntry[tid] = (uint16_t)(entry == 0xFFFFFFFFu ? (uint32_t)p : entry);
+        S.segExit[tid] = (uint16_t)p;
+        S.segN[tid] = (uint16_t)(cnt | (bad ? 0x8000u : 0u));
+        S.segOut[tid] = ob;
+    };
+    if (tid < NS) walk(segStart > DT_WARM ? segStart - DT_WARM : 0);
+    for (int round = 0;; round++) {
+        __syncthreads();
+        if (round == 0) DT_PROF(1);
+        uint32_t e = 0;
+        bool wrong = false;
+        if (tid >= 1 && tid < NS) { e = S.segExit[tid - 1]; wrong = S.segEntry[tid] != e; }
+        if (!__syncthreads_or(wrong)) break;
+        if (round > NS + 1) return -1;                          // cannot happen: lane t is final after round t
+        if (wrong) {
+            walk((int)e);
+#ifdef K4_DT_PROFILE
+            atomicAdd(&g_decode_stats[3], 1ull);
+#endif
+        }
+        DT_PROF_COUNT(16, 1);
+    }
+    DT_PROF(2);
+
+    // ---- 2. block-wide exclusive scan of (sequence count, output bytes) per segment ----------------
+    uint32_t cIn = 0, oIn = 0, badSeg = 0;
+    if (tid < NS) { const uint32_t v = S.segN[tid]; cIn = v & 0x7FFFu; badSeg = v >> 15; oIn = S.segOut[tid]; }
+    uint32_t cInc = cIn, oInc = oIn;
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+        const uint32_t c2 = __shfl_up_sync(FULL, cInc, dlt), o2 = __shfl_up_sync(FULL, oInc, dlt);
+        if (lane >= dlt) { cInc += c2; oInc += o2; }
+    }
+    if (lane == 31) { S.warpA[warp] = cInc; S.warpB[warp] = oInc; }
+    const bool anyBad = __syncthreads_or(badSeg != 0);
+    uint32_t wc = lane < DT_WARPS ? S.warpA[lane] : 0u, wo = lane < DT_WARPS ? S.warpB[lane] : 0u;
+#pragma unroll
+    for (int dlt = 1; dlt < DT_WARPS; dlt <<= 1) {
+        const uint32_t c2 = __shfl_up_sync(FULL, wc, dlt), o2 = __shfl_up_sync(FULL, wo, dlt);
+        if (lane >= dlt) { wc += c2; wo += o2; }
+    }
+    const int N = (int)__shfl_sync(FULL, wc, DT_WARPS - 1);     // sequences in the block
+    const int O = (int)__shfl_sync(FULL, wo, DT_WARPS - 1);     // decoded size
+    const uint32_t cBase = warp ? __shfl_sync(FULL, wc, warp - 1) : 0u;
+    const uint32_t oBase = warp ? __shfl_sync(FULL, wo, warp - 1) : 0u;
+    if (anyBad || N <= 0 || N > DT_NMAX || O <= 0 || O > TILE_BYTES || O > cap) return -1;
+    DT_PROF(3);
+
+    // descriptors: desc[i] = tokenPos | outPos << 16, in the tail of the tile
+    uint32_t* const desc = reinterpret_cast<uint32_t*>(S.tile + TILE_BYTES + TILE_PAD) - N;
+    if (tid < NS) {
+        int p = (int)S.segEntry[tid];
+        uint32_t idx = cBase + cInc - cIn;
+        int op = (int)(oBase + oInc - oIn);
+        while (p < segEnd) {
+            int lit, litPos, ml, off, nx; uint32_t fl;
+            seq_header<false>(stage4, stg, shift, p, n, lit, litPos, ml, off, nx, fl);
+            desc[idx++] = (uint32_t)p | ((uint32_t)(op < 65535 ? op : 65535) << 16);
+            op += lit + ml;
+            p = nx;
         }
     }
-    for (int i = threadIdx.x; i < TILE_BYTES / 32; i += COPY_THREADS) S.ready[i] = 0;
     __syncthreads();
+    DT_PROF(4);
 
-    // ---- batches: one sequence per lane -----------------------------------------------------------
-    int piecesSeen = 0;                                   // staged pieces this warp has waited for
-    uint32_t descNext = (warp < nbatch && warp * 32 + lane < nseq) ? __ldg(d + warp * 32 + lane) : 0u;
-    for (int bt = warp; bt < nbatch; bt += COPY_WARPS) {
-        const int k = bt * 32 + lane;
-        const bool valid = k < nseq;
-        const uint32_t desc = descNext;
-        {   // prefetch this warp's next descriptors
-            const int kn = k + COPY_WARPS * 32;
-            descNext = (kn < nseq) ? __ldg(d + kn) : 0u;
-        }
-        const uint32_t tokPos = desc & 0xFFFFu;
-        const int dst = (int)(desc >> 16);
-        // the staged pieces holding this batch's sequence headers (a header = token + length bytes,
-        // at most ~260 bytes for a 64 KiB block); literal extents are waited for below
-        {
-            const int lastTok = __reduce_max_sync(FULL, valid ? (int)tokPos : 0);
-            int needPieces = (lastTok + 600 + shift + STAGE_PIECE - 1) / STAGE_PIECE;
-            if (needPieces > npieces) needPieces = npieces;
-            while (piecesSeen < needPieces) { mbar_wait(&S.bar[piecesSeen], 0); piecesSeen++; }
-        }
+    // ---- 3. steps of DT_K sequences ----------------------------------------------------------------
+    const int tshift = (int)(reinterpret_cast<uintptr_t>(gdst) & 15);
+    uint8_t* const T = S.tile + tshift;                          // T[op] is output byte op
+    const int nsteps = (N + DT_K - 1) / DT_K;
+    uint32_t dCur = tid < N ? desc[tid] : 0u;
+    int Sr = 0;                                                  // output position where the step begins
+    for (int r = 0; r < nsteps; r++) {
+        const int i = r * DT_K + tid;
+        const bool valid = i < N;
+        const uint32_t dNext = i + DT_K < N ? desc[i + DT_K] : 0u;   // intact until the next step writes
+        const int SrNext = (r + 1) * DT_K < N ? (int)(desc[(r + 1) * DT_K] >> 16) : O;
 
-        // sequence header (lengths already validated by the parse kernel)
-        int lit = 0, ml = 0, offset = 0;
-        uint32_t litSrc = 0;
-        bool hasMatch = false;
+        // sequence header, with the reference's accept tests (conservative: see file header)
+        int lit = 0, ml = 0, off = 0, litPos = 0, op = 0;
+        bool bad = false;
         if (valid) {
-            const uint32_t token = stg[tokPos];
-            uint32_t p = tokPos + 1;
-            lit = (int)(token >> 4);
-            if (lit == 15) {                                   // LZ4_readVLE incl. its early stop
-                for (;;) {
-                    const uint32_t s = stg[p]; p++;
-                    lit += (int)s;
-                    if ((int)p >= n - 15) break;
-                    if (s != 255) break;
-                }
+            const int tp = (int)(dCur & 0xFFFFu);
+            op = (int)(dCur >> 16);
+            int nx; uint32_t fl;
+            seq_header<true>(stage4, stg, shift, tp, n, lit, litPos, ml, off, nx, fl);
+            bad = (fl & (SQ_EDGE | SQ_BAD)) != 0;
+            if (i == N - 1) {                                    // terminal: LL64.dec.cs:247-294
+                if (!(fl & SQ_LAST) || op + lit > cap) bad = true;
+            } else {
+                if ((fl & SQ_LAST) || litPos + lit > n - 8 || op + lit > cap - MFLIMIT) bad = true;   // :247
+                if (off == 0 || off > op + lit || op + lit + ml > cap - LASTLITERALS) bad = true;     // :338, :427-433
             }
-            litSrc = p;
-            hasMatch = !(bi.lastIsTerminal && k == nseq - 1);
+            if (bad) { lit = 0; ml = 0; }
         }
-        {   // every staged byte this batch reads (literals, then offset + match length bytes)
-            const int endMax = __reduce_max_sync(FULL, valid ? (int)litSrc + lit + 300 : 0);
-            int needPieces = (endMax + shift + STAGE_PIECE - 1) / STAGE_PIECE;
-            if (needPieces > npieces) needPieces = npieces;
-            while (piecesSeen < needPieces) { mbar_wait(&S.bar[piecesSeen], 0); piecesSeen++; }
-        }
-        if (hasMatch) {
-            uint32_t p = litSrc + (uint32_t)lit;
-            offset = (int)stg[p] | ((int)stg[p + 1] << 8);
-            p += 2;
-            ml = (int)(stg[tokPos] & 15);
-            if (ml == 15) {
-                for (;;) { const uint32_t s = stg[p]; p++; ml += (int)s; if (s != 255) break; }
-            }
-            ml += MINMATCH;
-        }
-        // helpers on the byte-readiness bitmap -----------------------------------------------------
-        // mark [a, a+len) final (len <= 32: at most two words)
-        auto publish_short = [&](const int a, const int len) {
-            if (len > 0) {
-                const unsigned long long m = ((len >= 64 ? 0ull : (1ull << len)) - 1ull) << (a & 31);
-                uint32_t* w = const_cast<uint32_t*>(&S.ready[a >> 5]);
-                atomicOr(w, (uint32_t)m);
-                if ((uint32_t)(m >> 32)) atomicOr(w + 1, (uint32_t)(m >> 32));
-            }
-        };
-        // are all bytes of [a, a+len) final? (len <= 32)
-        auto ready_short = [&](const int a, const int len) -> bool {
-            if (len <= 0) return true;
-            const unsigned long long m = ((1ull << len) - 1ull) << (a & 31);
-            const uint32_t lo32 = (uint32_t)m, hi32 = (uint32_t)(m >> 32);
-            bool r = (S.ready[a >> 5] & lo32) == lo32;
-            if (hi32) r = r && ((S.ready[(a >> 5) + 1] & hi32) == hi32);
-            return r;
-        };
-        // whole-warp versions for runs of any length (uniform arguments)
-        auto publish_long = [&](const int a, const int len) {
-            const int w0 = a >> 5, w1 = (a + len - 1) >> 5;
-            for (int w = w0 + lane; w <= w1; w += 32) {
-                const int b0 = (w << 5) > a ? (w << 5) : a;
-                const int b1 = ((w + 1) << 5) < (a + len) ? ((w + 1) << 5) : (a + len);
-                const uint32_t m = (uint32_t)(((1ull << (b1 - b0)) - 1ull) << (b0 & 31));
-                atomicOr(const_cast<uint32_t*>(&S.ready[w]), m);
-            }
-        };
-        auto ready_long = [&](const int a, const int len) -> bool {
-            const int w0 = a >> 5, w1 = (a + len - 1) >> 5;
-            bool r = true;
-            for (int w = w0 + lane; w <= w1; w += 32) {
-                const int b0 = (w << 5) > a ? (w << 5) : a;
-                const int b1 = ((w + 1) << 5) < (a + len) ? ((w + 1) << 5) : (a + len);
-                const uint32_t m = (uint32_t)(((1ull << (b1 - b0)) - 1ull) << (b0 & 31));
-                r = r && ((S.ready[w] & m) == m);
-            }
-            return __all_sync(FULL, r);
-        };
+        DT_PROF(5);
 
-        // ---- literals: short runs lane-parallel (all loads, then all stores), long runs by the warp -----
+        // classification of the match
+        const int d = op + lit;                                  // match destination
+        const int a = d - off;                                   // match source
+        const int srcEnd = a + ml < d ? a + ml : d;              // bytes read from outside the match itself: [a, srcEnd)
+        const bool nearM = ml > 0 && srcEnd > Sr;
+        const bool farM = ml > 0 && !nearM;
+        const bool farPieces = farM && off >= ml && ml < DT_HUGE;   // plain copy of moderate size
+        const bool litPieces = lit < DT_HUGE;
+
+        // literals and far matches as evenly distributed pieces
         {
-            const int shortLit = lit < 15 ? lit : 0;
-            const int mx = __reduce_max_sync(FULL, shortLit);
-            if (mx > 0) {
-                uint8_t v[14];
-                if (mx <= 7) {
-#pragma unroll
-                    for (int j = 0; j < 7; j++) if (j < shortLit) v[j] = stg[litSrc + j];
-#pragma unroll
-                    for (int j = 0; j < 7; j++) if (j < shortLit) tile[dst + j] = v[j];
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 14; j++) if (j < shortLit) v[j] = stg[litSrc + j];
-#pragma unroll
-                    for (int j = 0; j < 14; j++) if (j < shortLit) tile[dst + j] = v[j];
-                }
-                __threadfence_block();
-                publish_short(dst, shortLit);
-            }
-            unsigned longMask = __ballot_sync(FULL, lit >= 15);
-            while (longMask) {
-                const int l = __ffs(longMask) - 1;
-                longMask &= longMask - 1;
-                const uint32_t s0 = __shfl_sync(FULL, litSrc, l);
-                const int d0 = __shfl_sync(FULL, dst, l);
-                const int len = __shfl_sync(FULL, lit, l);
-                for (int i = lane; i < len; i += 32) tile[d0 + i] = stg[s0 + i];
-                __threadfence_block();
-                __syncwarp();
-                publish_long(d0, len);
-            }
+            const int cl = litPieces ? (lit + DT_PIECE - 1) / DT_PIECE : 0;
+            const int cm = farPieces ? (ml + DT_PIECE - 1) / DT_PIECE : 0;
+            const uint32_t P1 = (uint32_t)litPos | ((uint32_t)op << 16);
+            const uint32_t P2 = (uint32_t)(litPieces ? lit : 0) | ((uint32_t)(farPieces ? ml : 0) << 16);
+            const uint32_t P3 = (uint32_t)off | ((uint32_t)cl << 16);
+            warp_expand(cl + cm, lane, [&](const int owner, const int j, const bool live) {
+                const uint32_t p1 = __shfl_sync(FULL, P1, owner), p2 = __shfl_sync(FULL, P2, owner),
+                               p3 = __shfl_sync(FULL, P3, owner);
+                const int oLitPos = (int)(p1 & 0xFFFFu), oOp = (int)(p1 >> 16);
+                const int oLit = (int)(p2 & 0xFFFFu), oMl = (int)(p2 >> 16);
+                const int oOff = (int)(p3 & 0xFFFFu), oCl = (int)(p3 >> 16);
+                const bool isLit = j < oCl;
+                const int k = (isLit ? j : j - oCl) * DT_PIECE;
+                const int run = isLit ? oLit : oMl;
+                int len = run - k; len = len > DT_PIECE ? DT_PIECE : len;
+                if (!live) len = 0;
+                const int dpos = (isLit ? oOp : oOp + oLit) + k;
+                const uint8_t* sp = isLit ? stg + oLitPos + k : T + dpos - oOff;
+                piece_copy(T + dpos, sp, len);
+            });
         }
+        DT_PROF(6);
+        // the rest by the whole warp: huge literal runs, overlapping or huge far matches
+        for (unsigned m = __ballot_sync(FULL, !litPieces); m; m &= m - 1) {
+            const int l = __ffs(m) - 1;
+            warp_copy(T + __shfl_sync(FULL, op, l), stg + __shfl_sync(FULL, litPos, l), __shfl_sync(FULL, lit, l), lane);
+        }
+        for (unsigned m = __ballot_sync(FULL, farM && !farPieces); m; m &= m - 1) {
+            const int l = __ffs(m) - 1;
+            warp_copy_match_smem(T + __shfl_sync(FULL, d, l), __shfl_sync(FULL, off, l), __shfl_sync(FULL, ml, l), lane);
+        }
+        const unsigned nearBallot = __ballot_sync(FULL, nearM);
+        if (lane == 0) S.nearCnt[r & 1][warp] = (uint32_t)__popc(nearBallot);
+        DT_PROF(7);
+        if (__syncthreads_or(bad)) return -1;                    // barrier #1: literals and far matches are final
+        DT_PROF(8);
+        DT_PROF_COUNT(17, 1);
 
-        // ---- matches: exact byte-level dependencies ---------------------------------------------------
-        const int mdst = dst + lit;
-        const int msrc = mdst - offset;
-        // bytes actually read: an overlapping match (offset < ml) only reads [msrc, mdst)
-        const int srcLen = hasMatch ? (offset == 0 ? 0 : (offset < ml ? offset : ml)) : 0;
-        unsigned backoff = 16u;
-        bool pendS = hasMatch && ml <= 18;                 // short: lane-parallel
-        unsigned pendL = __ballot_sync(FULL, hasMatch && ml > 18);   // long: whole warp, one at a time
-        for (;;) {
-            bool progress = false;
-            // short matches whose source bytes are all final
-            const bool go = pendS && (WAITMODE == 2 || ready_short(msrc, srcLen));
-            if (__any_sync(FULL, go)) {
-                __threadfence_block();                     // acquire the flagged bytes
-                {   // non-overlapping: all loads first, then all stores
-                    const int m1 = (go && offset >= ml) ? ml : 0;
-                    const int mx = __reduce_max_sync(FULL, m1);
-                    if (mx > 0) {
-                        uint8_t v[18];
-                        if (mx <= 8) {
+        // near matches: sorted interval list, one thread per entry, rounds
+        uint32_t nc = lane < DT_WARPS ? S.nearCnt[r & 1][lane] : 0u;
 #pragma unroll
-                            for (int j = 0; j < 8; j++) if (j < m1) v[j] = tile[msrc + j];
-#pragma unroll
-                            for (int j = 0; j < 8; j++) if (j < m1) tile[mdst + j] = v[j];
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 18; j++) if (j < m1) v[j] = tile[msrc + j];
-#pragma unroll
-                            for (int j = 0; j < 18; j++) if (j < m1) tile[mdst + j] = v[j];
+        for (int dlt = 1; dlt < DT_WARPS; dlt <<= 1) {
+            const uint32_t c2 = __shfl_up_sync(FULL, nc, dlt);
+            if (lane >= dlt) nc += c2;
+        }
+        const int nearTotal = (int)__shfl_sync(FULL, nc, DT_WARPS - 1);
+        if (nearTotal > 0) {
+            const int nearBase = warp ? (int)__shfl_sync(FULL, nc, warp - 1) : 0;   // all lanes: no shuffle under divergence
+            if (nearM) {
+                const int me = nearBase + __popc(nearBallot & ((1u << lane) - 1u));
+                S.nearIv[me] = (uint32_t)d | ((uint32_t)(d + ml - 1) << 16);
+                S.nearOff[me] = (uint16_t)off;
+                S.nearFlag[me] = 1;
+            }
+            __syncthreads();                                     // barrier #2: list complete
+            // entry `tid` of the list is mine from here on
+            const bool mine = tid < nearTotal;
+            int nd = 0, nml = 0, noff = 1, lo = 0, hi = 0;
+            if (mine) {
+                const uint32_t iv = S.nearIv[tid];
+                nd = (int)(iv & 0xFFFFu); nml = (int)(iv >> 16) - nd + 1; noff = (int)S.nearOff[tid];
+                const int na = nd - noff;
+                const int nSrcEnd = na + nml < nd ? na + nml : nd;
+                // pending intervals before mine that intersect my source [na, nSrcEnd)
+                int x = 0, y = tid;
+                while (x < y) { const int mid = (x + y) >> 1; if ((int)(S.nearIv[mid] >> 16) >= na) y = mid; else x = mid + 1; }
+                lo = x; hi = lo;
+                while (hi < tid && (int)(S.nearIv[hi] & 0xFFFFu) < nSrcEnd) hi++;
+            }
+            bool pend = mine;
+            const bool plain = noff >= nml && nml < DT_HUGE;
+            DT_PROF(9);
+            const volatile uint8_t* flags = S.nearFlag;
+            const bool warpHasWork = warp * 32 < nearTotal;
+            for (int round = 0;; round++) {
+                if (warpHasWork) {
+                    bool progress;
+                    do {
+                        bool go = pend;
+                        if (go) {
+                            while (lo < hi && !flags[lo]) lo++;
+                            go = lo >= hi;
                         }
-                    }
+                        __threadfence_block();                   // bytes behind the cleared flags
+                        {
+                            const uint32_t Q1 = (uint32_t)nd | ((uint32_t)nml << 16);
+                            warp_expand(go && plain ? (nml + DT_PIECE - 1) / DT_PIECE : 0, lane,
+                                        [&](const int owner, const int j, const bool live) {
+                                const uint32_t q1 = __shfl_sync(FULL, Q1, owner);
+                                const int oOff = __shfl_sync(FULL, noff, owner);
+                                const int k = j * DT_PIECE;
+                                int len = (int)(q1 >> 16) - k; len = len > DT_PIECE ? DT_PIECE : len;
+                                if (!live) len = 0;
+                                const int dpos = (int)(q1 & 0xFFFFu) + k;
+                                piece_copy(T + dpos, T + dpos - oOff, len);
+                            });
+                        }
+                        for (unsigned m = __ballot_sync(FULL, go && !plain); m; m &= m - 1) {
+                            const int l = __ffs(m) - 1;
+                            warp_copy_match_smem(T + __shfl_sync(FULL, nd, l), __shfl_sync(FULL, noff, l), __shfl_sync(FULL, nml, l), lane);
+                        }
+                        __threadfence_block();
+                        __syncwarp();
+                        if (go) { S.nearFlag[tid] = 0; pend = false; }
+                        __syncwarp();
+                        progress = __any_sync(FULL, go);
+                        DT_PROF_COUNT(19, 1);
+                    } while (progress && __any_sync(FULL, pend));
                 }
-                {   // overlapping (offset < ml) or offset 0: in-order byte loop per lane
-                    const int m2 = (go && offset < ml) ? ml : 0;
-                    const int mx = __reduce_max_sync(FULL, m2);
-                    if (offset > 0) { for (int j = 0; j < mx; j++) if (j < m2) tile[mdst + j] = tile[msrc + j]; }
-                    else            { for (int j = 0; j < mx; j++) if (j < m2) tile[mdst + j] = 0; }
-                }
-                __threadfence_block();
-                if (go) publish_short(mdst, ml);
-                pendS = pendS && !go;
-                progress = true;
+                DT_PROF(10);
+                const bool more = __syncthreads_or(pend);
+                DT_PROF(11);
+                DT_PROF_COUNT(18, 1);
+                if (!more) break;
+                if (round > DT_K + 2) return -1;                 // cannot happen: each round retires the first pending match
             }
-            // long matches
-            unsigned m = pendL;
-            while (m) {
-                const int l = __ffs(m) - 1;
-                m &= m - 1;
-                const int s0 = __shfl_sync(FULL, msrc, l);
-                const int d0 = __shfl_sync(FULL, mdst, l);
-                const int len = __shfl_sync(FULL, ml, l);
-                const int sl = __shfl_sync(FULL, srcLen, l);
-                if (!(WAITMODE == 2 || sl == 0 || ready_long(s0, sl))) continue;
-                __threadfence_block();
-                const int off = d0 - s0;
-                if (off == 0)          for (int i = lane; i < len; i += 32) tile[d0 + i] = 0;
-                else if (off >= len)   for (int i = lane; i < len; i += 32) tile[d0 + i] = tile[s0 + i];
-                else                   for (int i = lane; i < len; i += 32) tile[d0 + i] = tile[s0 + (i % off)];
-                __threadfence_block();
-                __syncwarp();
-                publish_long(d0, len);
-                pendL &= ~(1u << l);
-                progress = true;
-            }
-            if (!__any_sync(FULL, pendS) && !pendL) break;
-            if (progress) backoff = 16u;
-            else if (WAITMODE == 1) { __nanosleep(backoff); if (backoff < 512u) backoff <<= 1; }   // nothing ready: back off
         }
+        dCur = dNext;
+        Sr = SrNext;
     }
+
+    // ---- tile -> global: ragged head and tail by threads, the aligned middle by one TMA bulk store ----
+    fence_async_smem();
     __syncthreads();
+    DT_PROF(12);
+    {
+        const int hRaw = (16 - tshift) & 15;
+        const int h = hRaw < O ? hRaw : O;
+        const int bulk = (O - h) & ~15;
+        if (tid < h) gdst[tid] = T[tid];
+        const int tail = O - h - bulk;
+        if (tid >= 32 && tid < 32 + tail) gdst[h + bulk + tid - 32] = T[h + bulk + tid - 32];
+        if (tid == 0 && bulk > 0) tma_store(gdst + h, T + h, bulk);
+    }
+    DT_PROF(13);
+    DT_PROF_COUNT(20, 1);
+    return O;
+}
 
-    // ---- tile -> global ------------------------------------------------------------------------------
-    uint8_t* gdst = dstBase + dstOff[b];
-    const int total = bi.outLen;
-    if ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0) {
-        const int bulk = total & ~15;
-        if (threadIdx.x == 0 && bulk > 0) tma_store_tile(gdst, tile, bulk);
-        for (int i = bulk + threadIdx.x; i < total; i += COPY_THREADS) gdst[i] = tile[i];
-    } else {
-        // unaligned destination: byte head up to 4-byte alignment, then words built from the tile
-        const int head = (int)((4 - (reinterpret_cast<uintptr_t>(gdst) & 3)) & 3);
-        const int h = head < total ? head : total;
-        for (int i = threadIdx.x; i < h; i += COPY_THREADS) gdst[i] = tile[i];
-        const int words = (total - h) >> 2;
-        uint32_t* g4 = reinterpret_cast<uint32_t*>(gdst + h);
-        for (int i = threadIdx.x; i < words; i += COPY_THREADS) {
-            const uint8_t* s = tile + h + 4 * i;
-            g4[i] = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24);
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+// Work-list entry of the second and third launch: block index, bit 31 = "exact decoder only".
+constexpr uint32_t WL_GENERIC = 0x80000000u;
+
+struct DecodeLists {
+    uint32_t* big;      // blocks for the big-stage tile kernel
+    uint32_t* gen;      // blocks for the exact generic decoder
+    uint32_t* counts;   // [0] = entries in big, [1] = entries in gen
+};
+
+__device__ __forceinline__ void wl_push(uint32_t* list, uint32_t* count, uint32_t b) {
+    list[atomicAdd(count, 1u)] = b;
+}
+
+// LZ4Codec.Decode argument handling (LZ4Codec.cs:104-115, LL64.dec.cs:162-172); true when done
+__device__ __forceinline__ bool decode_trivial(int n, int cap, int32_t* outLen) {
+    if (n <= 0) { *outLen = 0; return true; }
+    if (cap <= 0) { *outLen = -1; return true; }
+    return false;
+}
+
+// launch 1: one CTA per block, small stage, two CTAs per SM
+__global__ void __launch_bounds__(DT_THREADS, 2)
+decode_tile_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restrict__ srcOff,
+                   const int32_t* __restrict__ srcLen, uint8_t* __restrict__ dstBase,
+                   const int64_t* __restrict__ dstOff, const int32_t* __restrict__ dstCap,
+                   int32_t* __restrict__ outLen, DecodeLists wl) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    TileSmem<STAGE_SMALL>& S = *reinterpret_cast<TileSmem<STAGE_SMALL>*>(smem_raw);
+    const int b = blockIdx.x;
+    const int n = srcLen[b], cap = dstCap[b];
+    if (n <= 0 || cap <= 0) { if (threadIdx.x == 0) decode_trivial(n, cap, &outLen[b]); return; }
+    const uint8_t* src = srcBase + srcOff[b];
+    const int shift = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+    if (n > DT_MAX_SRC) { if (threadIdx.x == 0) wl_push(wl.gen, &wl.counts[1], (uint32_t)b); return; }
+    if (shift + n + 16 > STAGE_SMALL) { if (threadIdx.x == 0) wl_push(wl.big, &wl.counts[0], (uint32_t)b); return; }
+    if (threadIdx.x == 0) mbar_init(&S.bar, 1);
+    __syncthreads();
+    uint32_t parity = 0;
+    const int r = tile_decode_block<STAGE_SMALL>(S, src, n, dstBase + dstOff[b], cap, parity);
+    if (threadIdx.x == 0) {
+        if (r > 0) { outLen[b] = r; atomicAdd(&g_decode_stats[0], 1ull); }
+        else wl_push(wl.gen, &wl.counts[1], (uint32_t)b);
+    }
+}
+
+// launch 2: persistent, one CTA per SM, big stage: blocks whose compressed size needs it
+__global__ void __launch_bounds__(DT_THREADS, 1)
+decode_tile_big_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restrict__ srcOff,
+                       const int32_t* __restrict__ srcLen, uint8_t* __restrict__ dstBase,
+                       const int64_t* __restrict__ dstOff, const int32_t* __restrict__ dstCap,
+                       int32_t* __restrict__ outLen, DecodeLists wl) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    TileSmem<STAGE_BIG>& S = *reinterpret_cast<TileSmem<STAGE_BIG>*>(smem_raw);
+    const uint32_t count = wl.counts[0];
+    if (blockIdx.x >= count) return;
+    if (threadIdx.x == 0) mbar_init(&S.bar, 1);
+    __syncthreads();
+    uint32_t parity = 0;
+    for (uint32_t e = blockIdx.x; e < count; e += gridDim.x) {
+        const int b = (int)wl.big[e];
+        const uint8_t* src = srcBase + srcOff[b];
+        const int r = tile_decode_block<STAGE_BIG>(S, src, srcLen[b], dstBase + dstOff[b], dstCap[b], parity);
+        if (threadIdx.x == 0) {
+            if (r > 0) { outLen[b] = r; atomicAdd(&g_decode_stats[1], 1ull); }
+            else wl_push(wl.gen, &wl.counts[1], (uint32_t)b);
         }
-        for (int i = h + 4 * words + threadIdx.x; i < total; i += COPY_THREADS) gdst[i] = tile[i];
+        __syncthreads();            // the tile and the stage are reused
+    }
+}
+
+// launch 3: persistent, warp per block: the exact decoder for everything the tile path declined
+__global__ void __launch_bounds__(128)
+decode_rest_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restrict__ srcOff,
+                   const int32_t* __restrict__ srcLen, uint8_t* __restrict__ dstBase,
+                   const int64_t* __restrict__ dstOff, const int32_t* __restrict__ dstCap,
+                   int32_t* __restrict__ outLen, DecodeLists wl) {
+    const uint32_t count = wl.counts[1];
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < count; e += nwarps) {
+        const int b = (int)wl.gen[e];
+        const int r = codec_decode_warp(srcBase + srcOff[b], srcLen[b], dstBase + dstOff[b], dstCap[b]);
+        if (lane_id() == 0) { outLen[b] = r; atomicAdd(&g_decode_stats[2], 1ull); }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// launcher
+// launcher (host)
 // ------------------------------------------------------------------------------------------------
-template <int STAGE, int W>
-inline void decode_copy_launch_t(const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen,
-                                 uint8_t* dstBase, const int64_t* dstOff, const int32_t* dstCap,
-                                 int32_t* outLen, const BlockInfo* info, const uint32_t* descs,
-                                 int first, int count, cudaStream_t st) {
-    static bool attr[64] = {false};                       // function attributes are per device
-    int dev = 0; cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) dev = 0;
-    if (!attr[dev]) {
-        cudaFuncSetAttribute(decode_copy_kernel<STAGE, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(CopySmem<STAGE>));
-        attr[dev] = true;
-    }
-    decode_copy_kernel<STAGE, W><<<count, COPY_THREADS, sizeof(CopySmem<STAGE>), st>>>(
-        srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, info, descs, first);
-}
+// Per-device state of the decoder: a PRIVATE stream-ordered memory pool for the work lists (the
+// process-wide default pool is never touched), the SM count, the kernels' shared-memory opt-in.
+struct DecodeDev {
+    std::once_flag once;
+    cudaMemPool_t pool = nullptr;
+    int sms = 0;
+    cudaError_t err = cudaSuccess;
+};
 
-inline void decode_tile_set_attrs() {}
-
-// returns the number of kernels launched, or -1 on a CUDA error (cudaGetLastError has it)
-inline int decode_tile_launch(const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen,
-                              uint8_t* dstBase, const int64_t* dstOff, const int32_t* dstCap,
-                              int32_t* outLen, int n, cudaStream_t st) {
-    static const int variant = [] { const char* e = getenv("K4LZ4_COPY_VARIANT"); return e ? atoi(e) : 0; }();
-    static const int subEnv = [] { const char* e = getenv("K4LZ4_SUB_BATCH"); return e ? atoi(e) : SUB_BATCH; }();
-    const int sub = n < subEnv ? n : subEnv;
-    {   // keep the stream-ordered pool's memory across calls (default: released at every sync)
-        static bool poolSet[64] = {false};
-        int dev = 0; cudaGetDevice(&dev);
-        if (dev >= 0 && dev < 64 && !poolSet[dev]) {
-            cudaMemPool_t pool; 
-            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-                unsigned long long thr = ~0ull;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+inline DecodeDev* decode_dev(int dev) {
+    static DecodeDev devs[64];
+    if (dev < 0 || dev >= 64) return nullptr;
+    DecodeDev* d = &devs[dev];
+    std::call_once(d->once, [d, dev] {
+        cudaError_t e = cudaDeviceGetAttribute(&d->sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(decode_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(TileSmem<STAGE_SMALL>));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(decode_tile_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(TileSmem<STAGE_BIG>));
+        if (e == cudaSuccess) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            e = cudaMemPoolCreate(&d->pool, &props);
+            if (e == cudaSuccess) {
+                unsigned long long keep = 64ull << 20;          // cache up to 64 MiB of work lists
+                cudaMemPoolSetAttribute(d->pool, cudaMemPoolAttrReleaseThreshold, &keep);
             }
-            poolSet[dev] = true;
         }
+        d->err = e;
+    });
+    return d;
+}
+
+// Enqueues the decode of n blocks on `st` (current device).  Returns the number of kernels
+// launched, or -1 with *err set.
+inline int decode_launch(const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen,
+                         uint8_t* dstBase, const int64_t* dstOff, const int32_t* dstCap,
+                         int32_t* outLen, int n, cudaStream_t st, cudaError_t* err) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    DecodeDev* D = decode_dev(dev);
+    if (!D || D->err != cudaSuccess) { *err = D ? D->err : cudaErrorInvalidDevice; return -1; }
+    uint32_t* scratch = nullptr;
+    cudaError_t e = cudaMallocFromPoolAsync((void**)&scratch, ((size_t)2 * n + 4) * sizeof(uint32_t), D->pool, st);
+    if (e != cudaSuccess) { *err = e; return -1; }
+    DecodeLists wl;
+    wl.counts = scratch;
+    wl.big = scratch + 4;
+    wl.gen = scratch + 4 + n;
+    e = cudaMemsetAsync(wl.counts, 0, 4 * sizeof(uint32_t), st);
+    if (e == cudaSuccess) {
+        decode_tile_kernel<<<n, DT_THREADS, sizeof(TileSmem<STAGE_SMALL>), st>>>(
+            srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, wl);
+        const int gridBig = n < D->sms ? n : D->sms;
+        decode_tile_big_kernel<<<gridBig, DT_THREADS, sizeof(TileSmem<STAGE_BIG>), st>>>(
+            srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, wl);
+        const int want = (n + 3) / 4;
+        const int gridRest = want < D->sms * 8 ? want : D->sms * 8;
+        decode_rest_kernel<<<gridRest, 128, 0, st>>>(srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, wl);
+        e = cudaGetLastError();
     }
-    uint32_t* descs = nullptr;
-    BlockInfo* info = nullptr;
-    if (cudaMallocAsync(&descs, (size_t)sub * DESC_CAP * sizeof(uint32_t), st) != cudaSuccess) return -1;
-    if (cudaMallocAsync(&info, (size_t)sub * sizeof(BlockInfo), st) != cudaSuccess) { cudaFreeAsync(descs, st); return -1; }
-    int launches = 0;
-    for (int first = 0; first < n; first += sub) {
-        const int count = (n - first) < sub ? (n - first) : sub;
-        decode_parse_kernel<<<(count + PARSE_THREADS - 1) / PARSE_THREADS, PARSE_THREADS, 0, st>>>(
-            srcBase, srcOff, srcLen, dstCap, outLen, info, descs, first, count);
-        launches++;
-#define K4_COPY(STG, W) decode_copy_launch_t<STG, W>(srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, info, descs, first, count, st)
-        switch (variant) {
-        case 2: K4_COPY(STAGE_SMALL, 2); K4_COPY(STAGE_BIG, 2); launches += 2; break;   // no waiting (tools/dbench.py only)
-        case 9: break;                                                                   // parse only (tools/dbench.py only)
-        default: K4_COPY(STAGE_SMALL, 1); K4_COPY(STAGE_BIG, 1); launches += 2; break;
-        }
-#undef K4_COPY
-    }
-    cudaFreeAsync(descs, st);
-    cudaFreeAsync(info, st);
-    return launches;
+    cudaFreeAsync(scratch, st);
+    if (e != cudaSuccess) { *err = e; return -1; }
+    return 3;
 }
 
 }  // namespace k4

@@ -18,6 +18,9 @@
 namespace k4 {
 
 constexpr int ENC_TABLE_BYTES = 16384;   // LZ4_stream_t hash table, LL.types.cs:18-39
+constexpr int ENC_FLAG_X32 = 0x100;      // `level` bit: reproduce the 32-bit engine (LL32) for inputs >= 65 547 bytes
+constexpr int ENC_TAG_BYTES = 8192;      // one filter byte per u16 slot (encode_tile.cuh)
+constexpr int ENC_SLOT_BYTES = ENC_TABLE_BYTES + ENC_TAG_BYTES;   // shared memory per warp
 
 struct EncCtx {
     const uint8_t* src;
@@ -212,21 +215,6 @@ __device__ __forceinline__ int codec_encode_warp(const uint8_t* src, int n, uint
     return r <= 0 ? -1 : r;
 }
 
-constexpr int ENC_WARPS_PER_CTA = 7;   // 7 x 16 KiB tables = 112 KiB: two CTAs (14 blocks in flight) per SM
-
-__global__ void __launch_bounds__(ENC_WARPS_PER_CTA * 32)
-encode_generic_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restrict__ srcOff,
-                      const int32_t* __restrict__ srcLen, uint8_t* __restrict__ dstBase,
-                      const int64_t* __restrict__ dstOff, const int32_t* __restrict__ dstCap,
-                      int32_t* __restrict__ outLen, int nBlocks, int level, int enforce32) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const int wInCta = threadIdx.x >> 5;
-    const int b = blockIdx.x * ENC_WARPS_PER_CTA + wInCta;
-    if (b >= nBlocks) return;
-    void* table = smem + wInCta * ENC_TABLE_BYTES;
-    int r = codec_encode_warp(srcBase + srcOff[b], srcLen[b], dstBase + dstOff[b], dstCap[b],
-                              level, table, enforce32 != 0);
-    if (lane_id() == 0) outLen[b] = r;
-}
+constexpr int ENC_WARPS_PER_CTA = 9;   // 9 x 24 KiB (table + tags) = 216 KiB: one CTA, nine blocks in flight per SM
 
 }  // namespace k4

@@ -22,8 +22,6 @@
 
 namespace k4 {
 
-constexpr int ENCT_STAGE = 65536 + 64;            // block bytes + alignment slack / read-ahead pad
-constexpr int ENCT_SMEM = ENCT_STAGE + ENC_TABLE_BYTES + 16;
 
 __device__ __forceinline__ uint32_t lds_u32u(const uint8_t* p) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
@@ -48,12 +46,21 @@ __device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* 
                                 uint8_t* __restrict__ dst, const int cap, const int hardCap, uint16_t* table) {
     const int lane = lane_id();
     const int64_t hard = hardCap;       // physical write bound (pickler, see pickle.cuh); 0x7fffffff otherwise
-    {   // LZ4_initStream: zero the table (LL.tools.cs:235-239)
+#define RD32(p) (STAGED ? lds_u32u(sin + (p)) : ldg_u32u(src + (p)))
+    // Tag filter.  Next to every 16-bit slot sits an 8-bit tag: bits 11..18 of the same product whose
+    // bits 19..31 are the hash, taken from the 4 bytes AT the stored position.  Equal 4-byte values
+    // have equal tags, so a probe only has to fetch its candidate's bytes (a scattered global load,
+    // 32 of them per batch otherwise: the kernel was bound by L1 wavefronts) when the tags agree --
+    // one probe in 256 by chance, plus the true hits.  The decision `hit` is unchanged.
+    uint8_t* const tags = reinterpret_cast<uint8_t*>(table) + ENC_TABLE_BYTES;
+    {   // LZ4_initStream: zero the table (LL.tools.cs:235-239); every slot then "holds" position 0
         uint4* t = reinterpret_cast<uint4*>(table);
         for (int i = lane; i < ENC_TABLE_BYTES / 16; i += 32) t[i] = make_uint4(0, 0, 0, 0);
+        const uint32_t t0 = n >= 4 ? (((RD32(0) * 2654435761u) >> 11) & 0xFFu) * 0x01010101u : 0u;
+        uint4* g = reinterpret_cast<uint4*>(tags);
+        for (int i = lane; i < ENC_TAG_BYTES / 16; i += 32) g[i] = make_uint4(t0, t0, t0, t0);
         __syncwarp();
     }
-#define RD32(p) (STAGED ? lds_u32u(sin + (p)) : ldg_u32u(src + (p)))
 #define RD8(p) (STAGED ? (uint32_t)sin[(p)] : (uint32_t)__ldg(src + (p)))
     const bool limited = !(cap >= max_output_size((int)n));                           // LL64.fast.cs:524
     const int64_t olimit = cap;
@@ -69,23 +76,28 @@ __device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* 
         uint32_t base = 1;              // position of search probe 0 of the current run
         for (;;) {
             // ---- one batch of up to 32 probes (App. A step 3, and step 8 as lane 0) -----------------
-            uint32_t h2 = 0xFFFFFFFFu;
-            if (post) h2 = hash4(RD32(ip - 2), 13);                     // put(ip-2), :394
+            uint32_t h2 = 0xFFFFFFFFu, tag2 = 0;
+            if (post) { const uint32_t p2 = RD32(ip - 2) * 2654435761u; h2 = p2 >> 19; tag2 = (p2 >> 11) & 0xFFu; }   // put(ip-2), :394
             const bool isPost = post && lane == 0;
             const uint32_t q = q0 + (uint32_t)lane - (post ? 1u : 0u);            // search-probe index (lanes >= 1 if post)
             const uint32_t pos = isPost ? ip : base + probe_advance(q);
             // a search probe executes only if the NEXT probe position stays <= mflimitPlusOne (:172)
             const bool valid = isPost || (base + probe_advance(q + 1) <= mfl1);
             const uint32_t v = valid ? RD32(pos) : 0u;
-            const uint32_t h = valid ? hash4(v, 13) : (0x10000u + (uint32_t)lane);
+            const uint32_t prod = v * 2654435761u;
+            const uint32_t h = valid ? prod >> 19 : (0x10000u + (uint32_t)lane);
+            const uint32_t tg = (prod >> 11) & 0xFFu;
             uint32_t cand = valid ? (uint32_t)table[h] : 0u;
-            if (h == h2) cand = ip - 2;                                           // sees the put(ip-2)
+            uint32_t ctag = valid ? (uint32_t)tags[h] : 0x100u;
+            if (h == h2) { cand = ip - 2; ctag = tag2; }                          // sees the put(ip-2)
             const unsigned peers = __match_any_sync(FULL, h);
             const unsigned earlier = peers & ((1u << lane) - 1u);
             const int fromLane = earlier ? 31 - __clz(earlier) : lane;
             const uint32_t fwdPos = __shfl_sync(FULL, pos, fromLane);
-            if (earlier) cand = fwdPos;                                           // sees the nearest earlier store
-            const bool hit = valid && (RD32(cand) == v);                // :228 (byU16: no distance test)
+            const uint32_t fwdTag = __shfl_sync(FULL, tg, fromLane);
+            if (earlier) { cand = fwdPos; ctag = fwdTag; }                        // sees the nearest earlier store
+            bool hit = false;
+            if (valid && ctag == tg) hit = RD32(cand) == v;             // :228 (byU16: no distance test)
             const unsigned hits = __ballot_sync(FULL, hit);
             const unsigned ends = __ballot_sync(FULL, !valid);
             const int f = hits ? __ffs(hits) - 1 : 32;
@@ -98,9 +110,9 @@ __device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* 
                 const bool doStore = valid && ((1u << lane) & upto) && !(lane < 31 ? later : 0u);
                 if (post) {
                     const unsigned same2 = __ballot_sync(FULL, valid && h == h2) & upto;
-                    if (lane == 0 && !same2) table[h2] = (uint16_t)(ip - 2);      // nobody overwrote the put(ip-2)
+                    if (lane == 0 && !same2) { table[h2] = (uint16_t)(ip - 2); tags[h2] = (uint8_t)tag2; }   // nobody overwrote the put(ip-2)
                 }
-                if (doStore) table[h] = (uint16_t)pos;
+                if (doStore) { table[h] = (uint16_t)pos; tags[h] = (uint8_t)tg; }
                 __syncwarp();
             }
             if (f == 32) {                                                        // 32 misses: keep searching
@@ -188,62 +200,6 @@ __device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* 
 #undef RD8
 }
 
-__global__ void __launch_bounds__(32)
-encode_tile_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restrict__ srcOff,
-                   const int32_t* __restrict__ srcLen, uint8_t* __restrict__ dstBase,
-                   const int64_t* __restrict__ dstOff, const int32_t* __restrict__ dstCap,
-                   int32_t* __restrict__ outLen, int nBlocks, int level) {
-    extern __shared__ __align__(128) uint8_t smem_enct[];
-    uint8_t* const smem = smem_enct;
-    uint8_t* stage = smem;
-    uint16_t* table = reinterpret_cast<uint16_t*>(smem + ENCT_STAGE);
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + ENCT_STAGE + ENC_TABLE_BYTES);
-    const int b = blockIdx.x;
-    const int lane = threadIdx.x;
-    if (b >= nBlocks) return;
-    const int n_ = srcLen[b];
-    const uint8_t* __restrict__ src = srcBase + srcOff[b];
-    uint8_t* __restrict__ dst = dstBase + dstOff[b];
-    const int cap = dstCap[b];
-    if (n_ <= 0) { if (lane == 0) outLen[b] = 0; return; }                       // LZ4Codec.cs:45-46
-    if (level >= 3) { if (lane == 0) outLen[b] = -2; return; }                   // HC/OPT delegate
-    if (n_ >= LIMIT_64K) {                                                        // byU32 case: generic warp encoder
-        const int r = encode_block_warp(src, n_, dst, cap, 0x7fffffff, table, false);
-        if (lane == 0) outLen[b] = r <= 0 ? -1 : r;
-        return;
-    }
-    const uint32_t n = (uint32_t)n_;
-    const int shift = (int)(reinterpret_cast<uintptr_t>(src) & 15);
-    const uint8_t* sin = stage + shift;                                           // sin[p] == src[p]
-
-    // ---- stage the block (TMA bulk, 16 KiB pieces on one mbarrier) and zero the table --------------
-    const int staged = ((int)n + shift + 15) & ~15;
-    if (lane == 0) {
-        const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(a) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(a), "r"(staged) : "memory");
-        for (int off = 0; off < staged; off += 16384) {
-            const int bytes = staged - off < 16384 ? staged - off : 16384;
-            const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(stage + off);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         :: "r"(sdst), "l"(src - shift + off), "r"(bytes), "r"(a) : "memory");
-        }
-    }
-    __syncwarp();
-    {
-        const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
-        uint32_t ok;
-        do {
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(a), "r"(0) : "memory");
-        } while (!ok);
-    }
-
-    const int result = encode_spec_warp<true>(src, sin, n, dst, cap, 0x7fffffff, table);
-    if (lane == 0) outLen[b] = result <= 0 ? -1 : result;                        // LZ4Codec.cs:51
-}
-
 // Global-memory variant: ENC_WARPS_PER_CTA blocks per CTA, only the 16 KiB tables in shared memory.
 __global__ void __launch_bounds__(ENC_WARPS_PER_CTA * 32)
 encode_spec_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restrict__ srcOff,
@@ -255,15 +211,17 @@ encode_spec_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restric
     const int b = blockIdx.x * ENC_WARPS_PER_CTA + wInCta;
     const int lane = lane_id();
     if (b >= nBlocks) return;
-    uint16_t* table = reinterpret_cast<uint16_t*>(smem_encs + wInCta * ENC_TABLE_BYTES);
+    uint16_t* table = reinterpret_cast<uint16_t*>(smem_encs + wInCta * ENC_SLOT_BYTES);
     const int n_ = srcLen[b];
     const uint8_t* __restrict__ src = srcBase + srcOff[b];
     uint8_t* __restrict__ dst = dstBase + dstOff[b];
     const int cap = dstCap[b];
     if (n_ <= 0) { if (lane == 0) outLen[b] = 0; return; }
+    const bool enforce32 = (level & ENC_FLAG_X32) != 0;   // LL.Enforce32 (LL.tools.cs:29): hash4 for the byU32 table
+    level &= 0xFF;
     if (level >= 3) { if (lane == 0) outLen[b] = -2; return; }
     int r;
-    if (n_ >= LIMIT_64K) r = encode_block_warp(src, n_, dst, cap, 0x7fffffff, table, false);
+    if (n_ >= LIMIT_64K) r = encode_block_warp(src, n_, dst, cap, 0x7fffffff, table, enforce32);
     else r = encode_spec_warp<false>(src, nullptr, (uint32_t)n_, dst, cap, 0x7fffffff, table);
     if (lane == 0) outLen[b] = r <= 0 ? -1 : r;
 }

@@ -7,8 +7,13 @@
 #include "../../../../include/k4lz4.h"
 
 #include <cuda_runtime.h>
+#if defined(__linux__)
+#include <sched.h>
+#endif
 
 #include <algorithm>
+#include <cctype>
+#include <cstdlib>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -28,6 +33,7 @@
 #include "pickle.cuh"
 #include "synth.cuh"
 #include "copy_blocks.cuh"
+#include "xxh32.cuh"
 
 namespace {
 
@@ -63,21 +69,17 @@ int device_count_cached() {
 
 // ---- kernel launchers (device pointers) ---------------------------------------------------
 
-enum Op { OP_ENCODE = 0, OP_DECODE = 1, OP_PICKLE = 2, OP_UNPICKLE = 3, OP_USIZE = 4 };
+enum Op { OP_ENCODE = 0, OP_DECODE = 1, OP_PICKLE = 2, OP_UNPICKLE = 3, OP_USIZE = 4, OP_PICKLEW = 5 };
 
 std::once_flag g_attr_once[64];
 
 void set_func_attrs(int dev) {
     if (dev < 0 || dev >= 64) return;
     std::call_once(g_attr_once[dev], [] {
-        cudaFuncSetAttribute(k4::encode_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             k4::ENC_WARPS_PER_CTA * k4::ENC_TABLE_BYTES);
         cudaFuncSetAttribute(k4::pickle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             k4::ENC_WARPS_PER_CTA * k4::ENC_TABLE_BYTES);
-        cudaFuncSetAttribute(k4::encode_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k4::ENCT_SMEM);
+                             k4::ENC_WARPS_PER_CTA * k4::ENC_SLOT_BYTES);
         cudaFuncSetAttribute(k4::encode_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             k4::ENC_WARPS_PER_CTA * k4::ENC_TABLE_BYTES);
-        k4::decode_tile_set_attrs();
+                             k4::ENC_WARPS_PER_CTA * k4::ENC_SLOT_BYTES);
     });
 }
 
@@ -94,36 +96,27 @@ cudaError_t launch_op(Op op, const DevArgs& a, cudaStream_t st) {
     set_func_attrs(dev);
     switch (op) {
     case OP_ENCODE: {
-        static const int encVariant = [] { const char* e = getenv("K4LZ4_ENC_VARIANT"); return e ? atoi(e) : 1; }();
-        if (encVariant == 0) {
-            const int ctas = (a.n + k4::ENC_WARPS_PER_CTA - 1) / k4::ENC_WARPS_PER_CTA;
-            k4::encode_generic_kernel<<<ctas, k4::ENC_WARPS_PER_CTA * 32,
-                                        k4::ENC_WARPS_PER_CTA * k4::ENC_TABLE_BYTES, st>>>(
-                a.srcBase, a.srcOff, a.srcLen, a.dstBase, a.dstOff, a.dstCap, a.outLen, a.n, a.level, 0);
-        } else if (encVariant == 2) {
-            k4::encode_tile_kernel<<<a.n, 32, k4::ENCT_SMEM, st>>>(
-                a.srcBase, a.srcOff, a.srcLen, a.dstBase, a.dstOff, a.dstCap, a.outLen, a.n, a.level);
-        } else {
-            const int ctas = (a.n + k4::ENC_WARPS_PER_CTA - 1) / k4::ENC_WARPS_PER_CTA;
-            k4::encode_spec_kernel<<<ctas, k4::ENC_WARPS_PER_CTA * 32,
-                                     k4::ENC_WARPS_PER_CTA * k4::ENC_TABLE_BYTES, st>>>(
-                a.srcBase, a.srcOff, a.srcLen, a.dstBase, a.dstOff, a.dstCap, a.outLen, a.n, a.level);
-        }
+        const int ctas = (a.n + k4::ENC_WARPS_PER_CTA - 1) / k4::ENC_WARPS_PER_CTA;
+        k4::encode_spec_kernel<<<ctas, k4::ENC_WARPS_PER_CTA * 32,
+                                 k4::ENC_WARPS_PER_CTA * k4::ENC_SLOT_BYTES, st>>>(
+            a.srcBase, a.srcOff, a.srcLen, a.dstBase, a.dstOff, a.dstCap, a.outLen, a.n, a.level);
         g_launches++;
         break;
     }
     case OP_DECODE: {
-        const int nl = k4::decode_tile_launch(a.srcBase, a.srcOff, a.srcLen, a.dstBase, a.dstOff,
-                                              a.dstCap, a.outLen, a.n, st);
-        if (nl < 0) { cudaError_t e = cudaGetLastError(); return e != cudaSuccess ? e : cudaErrorMemoryAllocation; }
+        cudaError_t de = cudaSuccess;
+        const int nl = k4::decode_launch(a.srcBase, a.srcOff, a.srcLen, a.dstBase, a.dstOff,
+                                         a.dstCap, a.outLen, a.n, st, &de);
+        if (nl < 0) { (void)cudaGetLastError(); return de != cudaSuccess ? de : cudaErrorUnknown; }
         g_launches += nl;
         break;
     }
-    case OP_PICKLE: {
+    case OP_PICKLE:
+    case OP_PICKLEW: {
         const int ctas = (a.n + k4::ENC_WARPS_PER_CTA - 1) / k4::ENC_WARPS_PER_CTA;
         k4::pickle_kernel<<<ctas, k4::ENC_WARPS_PER_CTA * 32,
-                            k4::ENC_WARPS_PER_CTA * k4::ENC_TABLE_BYTES, st>>>(
-            a.srcBase, a.srcOff, a.srcLen, a.dstBase, a.dstOff, a.outLen, a.n, a.level);
+                            k4::ENC_WARPS_PER_CTA * k4::ENC_SLOT_BYTES, st>>>(
+            a.srcBase, a.srcOff, a.srcLen, a.dstBase, a.dstOff, a.outLen, a.n, a.level, op == OP_PICKLEW ? 1 : 0);
         g_launches++;
         break;
     }
@@ -201,8 +194,12 @@ struct HBuf {   // pinned host
 
 struct Slot {          // one in-flight chunk
     cudaStream_t stream = nullptr;
-    DBuf dSrc, dDst, dMeta;
-    HBuf hSrc, hDst, hMeta;
+    DBuf dSrc, dDst, dMeta, dPack, dPackOff;
+    HBuf hSrc, hDst, hMeta, hPackOff;
+    const int64_t* dDstOffArr = nullptr;   // device copies of the chunk's dst offsets / results (inside dMeta)
+    const int32_t* dOutLenArr = nullptr;
+    bool compact = false;             // stage 2 gathered the produced bytes on the device first
+    std::vector<int64_t> compactOff;  // ... and this is where block k starts in the staging buffer
     // description of the chunk that is in flight
     int64_t b0 = 0, b1 = 0;           // block range
     int64_t dLo = 0;                  // dst extent origin (direct mode) or 0 (packed mode)
@@ -238,7 +235,13 @@ struct HostArgs {
 inline int64_t dst_room(Op op, const HostArgs& a, int64_t i) {
     switch (op) {
     case OP_PICKLE: return a.srcLen[i] <= 0 ? 0 : (int64_t)a.srcLen[i] + 1;
+    case OP_PICKLEW: return a.srcLen[i] <= 0 ? 0 : (int64_t)a.srcLen[i] + 1 + k4::pickle_diff_width(a.srcLen[i]);
     case OP_USIZE: return 0;
+    case OP_ENCODE: {      // a capacity beyond compressBound(srcLen) behaves like compressBound (notLimited)
+        const int64_t cap = a.dstCap[i] < 0 ? 0 : a.dstCap[i];
+        const int64_t bound = a.srcLen[i] > 0 ? k4::max_output_size(a.srcLen[i]) : 0;
+        return cap < bound ? cap : bound;
+    }
     default: return a.dstCap[i] < 0 ? 0 : a.dstCap[i];
     }
 }
@@ -259,7 +262,8 @@ void scatter_chunk(Op op, const HostArgs& a, Slot& s) {
         for (int64_t i = lo; i < hi; i++) {
             const int32_t r = a.outLen[i];
             if (r <= 0) continue;
-            const int64_t off = s.dstPacked ? s.packedDstOff[i - s.b0] : a.dstOff[i] - s.dLo;
+            const int64_t off = s.compact ? s.compactOff[i - s.b0]
+                                : (s.dstPacked ? s.packedDstOff[i - s.b0] : a.dstOff[i] - s.dLo);
             memcpy(a.dstBase + a.dstOff[i], stage + off, (size_t)r);
         }
     });
@@ -275,6 +279,7 @@ int stage2_slot(Op op, const HostArgs& a, Slot& s) {
     memcpy(a.outLen + s.b0, (const int32_t*)s.hMeta.p, sizeof(int32_t) * (size_t)(s.b1 - s.b0));
     s.state = 2;
     s.direct = false;
+    s.compact = false;
     if (op == OP_USIZE || s.dstBytes <= 0) return K4LZ4_OK;
     bool full = !s.dstPacked;
     int64_t sum = 0;
@@ -288,8 +293,31 @@ int stage2_slot(Op op, const HostArgs& a, Slot& s) {
         s.direct = true;
         CU_TRY(cudaMemcpyAsync(a.dstBase + s.dLo, s.dDst.p, (size_t)s.dstBytes, cudaMemcpyDeviceToHost, s.stream));
     } else {
-        CU_TRY(s.hDst.ensure((size_t)s.dstBytes + 16));
-        CU_TRY(cudaMemcpyAsync(s.hDst.p, s.dDst.p, (size_t)s.dstBytes, cudaMemcpyDeviceToHost, s.stream));
+        // variable-length results (encode, pickle, short decodes): gather the produced bytes on the
+        // device (copy_blocks_kernel) so that only they cross PCIe, not the slots' slack
+        const int64_t nb = s.b1 - s.b0;
+        s.compactOff.resize((size_t)nb);
+        int64_t total = 0;
+        for (int64_t k = 0; k < nb; k++) {
+            s.compactOff[(size_t)k] = total;
+            const int32_t r = a.outLen[s.b0 + k];
+            if (r > 0) total += ((int64_t)r + 15) & ~int64_t(15);
+        }
+        s.compact = true;
+        s.dstBytes = total;
+        if (total == 0) return K4LZ4_OK;
+        CU_TRY(s.hPackOff.ensure((size_t)nb * 8));
+        CU_TRY(s.dPackOff.ensure((size_t)nb * 8));
+        CU_TRY(s.dPack.ensure((size_t)total + 16));
+        CU_TRY(s.hDst.ensure((size_t)total + 16));
+        memcpy(s.hPackOff.p, s.compactOff.data(), (size_t)nb * 8);
+        CU_TRY(cudaMemcpyAsync(s.dPackOff.p, s.hPackOff.p, (size_t)nb * 8, cudaMemcpyHostToDevice, s.stream));
+        k4::copy_blocks_kernel<<<(unsigned)nb, 256, 0, s.stream>>>(
+            (const uint8_t*)s.dDst.p, s.dDstOffArr, (uint8_t*)s.dPack.p, (const int64_t*)s.dPackOff.p,
+            s.dOutLenArr, (int)nb);
+        g_launches++;
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(s.hDst.p, s.dPack.p, (size_t)total, cudaMemcpyDeviceToHost, s.stream));
     }
     return K4LZ4_OK;
 }
@@ -349,7 +377,7 @@ int enqueue_chunk(Op op, const HostArgs& a, Slot& s, int64_t b0, int64_t b1) {
         const int64_t k = i - b0;
         const int64_t sl = src_size(a, i), dl = dst_room(op, a, i);
         hSrcLen[k] = a.srcLen[i];
-        hDstCap[k] = (op == OP_PICKLE || op == OP_USIZE) ? 0 : a.dstCap[i];
+        hDstCap[k] = (op == OP_PICKLE || op == OP_PICKLEW || op == OP_USIZE) ? 0 : (op == OP_ENCODE ? (int32_t)dl : a.dstCap[i]);
         if (srcPacked) {
             hSrcOff[k] = sp;
             if (sl > 0) memcpy((uint8_t*)s.hSrc.p + sp, a.srcBase + a.srcOff[i], (size_t)sl);
@@ -372,6 +400,8 @@ int enqueue_chunk(Op op, const HostArgs& a, Slot& s, int64_t b0, int64_t b1) {
     // outLen lands at the front of hMeta (offset arrays there are no longer needed once the
     // H2D above has been issued *and completed*; stream order guarantees that)
     CU_TRY(cudaMemcpyAsync(s.hMeta.p, dOutLen, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+    s.dDstOffArr = dDstOff;
+    s.dOutLenArr = dOutLen;
     s.state = 1;
     return K4LZ4_OK;
 }
@@ -429,6 +459,49 @@ void parallel_for_blocks(int64_t b0, int64_t b1, int64_t bytesHint,
     for (auto& t : th) t.join();
 }
 
+// Best effort: run the calling thread on the CPUs of the NUMA node GPU `dev` is attached to, so that
+// the pinned staging buffers it allocates (first touch) and its memcpy traffic stay node-local.
+// (HGX boards hang GPUs 0-3 and 4-7 off different sockets; staging through the far socket halves the
+// aggregate PCIe rate of an all-devices call.)
+void bind_thread_near_gpu(int dev) {
+#if defined(__linux__)
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), dev) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    for (char* c = bus; *c; c++) *c = (char)tolower(*c);
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    if (node < 0) return;
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return;
+    char list[4096] = {0};
+    const size_t got = fread(list, 1, sizeof(list) - 1, f);
+    fclose(f);
+    if (got == 0) return;
+    cpu_set_t want, have;
+    CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof(have), &have) != 0) return;
+    int any = 0;
+    for (char* p = list; *p;) {
+        char* e;
+        long lo = strtol(p, &e, 10), hi = lo;
+        if (e == p) break;
+        if (*e == '-') { p = e + 1; hi = strtol(p, &e, 10); }
+        for (long c = lo; c <= hi && c < CPU_SETSIZE; c++) if (CPU_ISSET((int)c, &have)) { CPU_SET((int)c, &want); any = 1; }
+        p = (*e == ',') ? e + 1 : e;
+        if (*e != ',' ) break;
+    }
+    if (any) sched_setaffinity(0, sizeof(want), &want);
+#else
+    (void)dev;
+#endif
+}
+
 int run_host(Op op, const HostArgs& a, int64_t n, int device) {
     const int ndev = device_count_cached();
     if (ndev <= 0) return fail(K4LZ4_E_NODEVICE, "no CUDA device available");
@@ -456,6 +529,7 @@ int run_host(Op op, const HostArgs& a, int64_t n, int device) {
     std::vector<std::thread> th;
     for (int d = 0; d < ndev; d++)
         th.emplace_back([&, d] {
+            bind_thread_near_gpu(d);
             rcs[d] = run_host_slice(op, a, cut[d], cut[d + 1], d);
             if (rcs[d] != K4LZ4_OK) errs[d] = t_err;
         });
@@ -479,6 +553,111 @@ int run(Op op, const uint8_t* srcBase, const int64_t* srcOff, const int32_t* src
     return fail(K4LZ4_E_ARG, "unknown memKind %d", memKind);
 }
 
+// ---- dictionary / partial decode: exactness first, simple staging ------
+
+struct GeneralArgs {
+    const uint8_t* srcBase; const int64_t* srcOff; const int32_t* srcLen;
+    uint8_t* dstBase; const int64_t* dstOff; const int32_t* dstCap;
+    const uint8_t* dictBase; const int64_t* dictOff; const int32_t* dictLen;   // all three may be null
+    int32_t* outLen; int64_t n; bool partial;
+};
+
+cudaError_t launch_general(const GeneralArgs& g, cudaStream_t st) {
+    if (g.n <= 0) return cudaSuccess;
+    const long long ctas = (g.n + 3) / 4;
+    k4::decode_general_kernel<<<(unsigned)ctas, 128, 0, st>>>(g.srcBase, g.srcOff, g.srcLen, g.dstBase, g.dstOff,
+                                                              g.dstCap, g.dictBase, g.dictOff, g.dictLen, g.outLen,
+                                                              (int)g.n, g.partial ? 1 : 0);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+struct DevMem {
+    void* p = nullptr;
+    ~DevMem() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+};
+
+// host pointers: pack the blocks of a chunk, one H2D per array, one kernel, one D2H, exact scatter
+int run_general_host(const GeneralArgs& g, int device) {
+    const int ndev = device_count_cached();
+    if (ndev <= 0) return fail(K4LZ4_E_NODEVICE, "no CUDA device available");
+    if (g.n < 0) return fail(K4LZ4_E_ARG, "negative block count");
+    if (g.n == 0) return K4LZ4_OK;
+    if (!g.srcBase || !g.srcOff || !g.srcLen || !g.dstBase || !g.dstOff || !g.dstCap || !g.outLen)
+        return fail(K4LZ4_E_ARG, "null pointer argument");
+    if (g.dictBase && (!g.dictOff || !g.dictLen)) return fail(K4LZ4_E_ARG, "null pointer argument");
+    const int dev = device >= 0 ? device : 0;
+    if (dev >= ndev) return fail(K4LZ4_E_ARG, "device %d out of range (%d visible)", dev, ndev);
+    DeviceGuard guard(dev);
+    if (!guard.ok) return fail(K4LZ4_E_CUDA, "cudaSetDevice(%d) failed", dev);
+    const int64_t CH = 256ll << 20;
+    int64_t i = 0;
+    while (i < g.n) {
+        int64_t j = i, bytes = 0;
+        while (j < g.n) {
+            const int64_t add = std::max<int64_t>(g.srcLen[j], 0) + std::max<int64_t>(g.dstCap[j], 0) +
+                                (g.dictBase ? std::max<int64_t>(g.dictLen[j], 0) : 0);
+            if (j > i && bytes + add > CH) break;
+            bytes += add; j++;
+        }
+        const int64_t nb = j - i;
+        std::vector<int64_t> so(nb), doff(nb), dio(nb);
+        std::vector<int32_t> sl(nb), dc(nb), dl(nb), res(nb);
+        int64_t sTot = 0, dTot = 0, diTot = 0;
+        for (int64_t k = 0; k < nb; k++) {
+            sl[k] = g.srcLen[i + k]; dc[k] = g.dstCap[i + k] < 0 ? 0 : g.dstCap[i + k];
+            dl[k] = g.dictBase ? std::max<int32_t>(g.dictLen[i + k], 0) : 0;
+            so[k] = sTot; doff[k] = dTot; dio[k] = diTot;
+            sTot += std::max<int32_t>(sl[k], 0); dTot += dc[k]; diTot += dl[k];
+        }
+        std::vector<uint8_t> hs((size_t)sTot + 16), hd((size_t)diTot + 16), ho((size_t)dTot + 16);
+        for (int64_t k = 0; k < nb; k++) {
+            if (sl[k] > 0) memcpy(hs.data() + so[k], g.srcBase + g.srcOff[i + k], (size_t)sl[k]);
+            if (dl[k] > 0) memcpy(hd.data() + dio[k], g.dictBase + g.dictOff[i + k], (size_t)dl[k]);
+        }
+        DevMem dS, dD, dO, dM;
+        CU_TRY(dS.alloc((size_t)sTot + 16)); CU_TRY(dD.alloc((size_t)diTot + 16)); CU_TRY(dO.alloc((size_t)dTot + 16));
+        CU_TRY(dM.alloc((size_t)nb * (8 * 3 + 4 * 4)));
+        int64_t* mSo = (int64_t*)dM.p; int64_t* mDo = mSo + nb; int64_t* mDio = mDo + nb;
+        int32_t* mSl = (int32_t*)(mDio + nb); int32_t* mDc = mSl + nb; int32_t* mDl = mDc + nb; int32_t* mRes = mDl + nb;
+        CU_TRY(cudaMemcpy(dS.p, hs.data(), (size_t)sTot, cudaMemcpyHostToDevice));
+        if (diTot) CU_TRY(cudaMemcpy(dD.p, hd.data(), (size_t)diTot, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(mSo, so.data(), (size_t)nb * 8, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(mDo, doff.data(), (size_t)nb * 8, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(mDio, dio.data(), (size_t)nb * 8, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(mSl, sl.data(), (size_t)nb * 4, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(mDc, dc.data(), (size_t)nb * 4, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(mDl, dl.data(), (size_t)nb * 4, cudaMemcpyHostToDevice));
+        GeneralArgs d{(const uint8_t*)dS.p, mSo, mSl, (uint8_t*)dO.p, mDo, mDc,
+                      g.dictBase ? (const uint8_t*)dD.p : nullptr, mDio, mDl, mRes, nb, g.partial};
+        CU_TRY(launch_general(d, nullptr));
+        CU_TRY(cudaMemcpy(res.data(), mRes, (size_t)nb * 4, cudaMemcpyDeviceToHost));
+        if (dTot) CU_TRY(cudaMemcpy(ho.data(), dO.p, (size_t)dTot, cudaMemcpyDeviceToHost));
+        for (int64_t k = 0; k < nb; k++) {
+            g.outLen[i + k] = res[k];
+            if (res[k] > 0) memcpy(g.dstBase + g.dstOff[i + k], ho.data() + doff[k], (size_t)res[k]);
+        }
+        i = j;
+    }
+    return K4LZ4_OK;
+}
+
+int run_general(const GeneralArgs& g, int memKind, void* stream, int device) {
+    if (memKind == K4LZ4_MEM_HOST) return run_general_host(g, device);
+    if (memKind != K4LZ4_MEM_DEVICE) return fail(K4LZ4_E_ARG, "unknown memKind %d", memKind);
+    if (device_count_cached() <= 0) return fail(K4LZ4_E_NODEVICE, "no CUDA device available");
+    if (g.n < 0 || g.n > INT32_MAX) return fail(K4LZ4_E_ARG, "bad block count");
+    if (g.n == 0) return K4LZ4_OK;
+    if (!g.srcBase || !g.srcOff || !g.srcLen || !g.dstBase || !g.dstOff || !g.dstCap || !g.outLen)
+        return fail(K4LZ4_E_ARG, "null pointer argument");
+    if (g.dictBase && (!g.dictOff || !g.dictLen)) return fail(K4LZ4_E_ARG, "null pointer argument");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(K4LZ4_E_CUDA, "cudaSetDevice(%d) failed", device);
+    CU_TRY(launch_general(g, (cudaStream_t)stream));
+    return K4LZ4_OK;
+}
+
 }  // namespace
 
 // ---- exported C ABI ------------------------------------------------------------------------
@@ -489,6 +668,31 @@ int32_t k4lz4_codec_version(void) { return 192; }
 int32_t k4lz4_device_count(void) { return device_count_cached(); }
 const char* k4lz4_last_error(void) { return t_err.c_str(); }
 int64_t k4lz4_launch_count(void) { return g_launches.load(); }
+
+int32_t k4lz4_decode_stats(int32_t device, uint64_t* out4, int32_t reset) {
+    if (device_count_cached() <= 0) return fail(K4LZ4_E_NODEVICE, "no CUDA device available");
+    if (!out4) return fail(K4LZ4_E_ARG, "null pointer argument");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(K4LZ4_E_CUDA, "cudaSetDevice(%d) failed", device);
+    unsigned long long v[4] = {0, 0, 0, 0};
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpyFromSymbol(v, k4::g_decode_stats, sizeof(v)));
+    for (int i = 0; i < 4; i++) out4[i] = v[i];
+    if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; CU_TRY(cudaMemcpyToSymbol(k4::g_decode_stats, z, sizeof(z))); }
+    return K4LZ4_OK;
+}
+
+#ifdef K4_DT_PROFILE
+// tools-only build: per-phase cycle sums of the tile decoder (scratch/, never shipped)
+__attribute__((visibility("default"))) int32_t k4lz4_debug_prof(uint64_t* out32, int32_t reset) {
+    unsigned long long v[32];
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpyFromSymbol(v, k4::g_decode_prof, sizeof(v)));
+    for (int i = 0; i < 32; i++) out32[i] = v[i];
+    if (reset) { unsigned long long z[32] = {0}; CU_TRY(cudaMemcpyToSymbol(k4::g_decode_prof, z, sizeof(z))); }
+    return K4LZ4_OK;
+}
+#endif
 
 int32_t k4lz4_max_output_size(int32_t length) { return k4::max_output_size(length); }
 int32_t k4lz4_pickle_bound(int32_t length) { return length <= 0 ? 0 : length + 1; }
@@ -512,10 +716,68 @@ int32_t k4lz4_decode(const uint8_t* src, int32_t srcLen, uint8_t* dst, int32_t d
     return rc != K4LZ4_OK ? rc : out;
 }
 
+int32_t k4lz4_decode_dict(const uint8_t* src, int32_t srcLen, uint8_t* dst, int32_t dstCap,
+                          const uint8_t* dict, int32_t dictLen) {
+    if (srcLen <= 0) return 0;                       // LZ4Codec.cs:150-151
+    if (!src || (!dst && dstCap > 0) || (!dict && dictLen > 0)) return fail(K4LZ4_E_ARG, "null pointer argument");
+    if (dstCap <= 0) return -1;
+    int64_t zero = 0; int32_t out = -1;
+    GeneralArgs g{src, &zero, &srcLen, dst, &zero, &dstCap, dictLen > 0 ? dict : nullptr, &zero, &dictLen, &out, 1, false};
+    const int rc = run_general(g, K4LZ4_MEM_HOST, nullptr, 0);
+    return rc != K4LZ4_OK ? rc : out;
+}
+
+int32_t k4lz4_partial_decode(const uint8_t* src, int32_t srcLen, uint8_t* dst, int32_t targetLen) {
+    if (srcLen <= 0) return 0;                       // LZ4Codec.cs:129-130
+    if (!src || (!dst && targetLen > 0)) return fail(K4LZ4_E_ARG, "null pointer argument");
+    if (targetLen <= 0) return -1;                   // engine returns 0 -> -1 (LZ4Codec.cs:135)
+    int64_t zero = 0; int32_t out = -1;
+    GeneralArgs g{src, &zero, &srcLen, dst, &zero, &targetLen, nullptr, nullptr, nullptr, &out, 1, true};
+    const int rc = run_general(g, K4LZ4_MEM_HOST, nullptr, 0);
+    return rc != K4LZ4_OK ? rc : out;
+}
+
+int32_t k4lz4_decode_dict_batch(const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen,
+                                uint8_t* dstBase, const int64_t* dstOff, const int32_t* dstCap,
+                                const uint8_t* dictBase, const int64_t* dictOff, const int32_t* dictLen,
+                                int32_t* outLen, int32_t nBlocks, int32_t memKind, void* cudaStream,
+                                int32_t device) {
+    GeneralArgs g{srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, dictBase, dictOff, dictLen, outLen, nBlocks, false};
+    return run_general(g, memKind, cudaStream, device);
+}
+
+int32_t k4lz4_partial_decode_batch(const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen,
+                                   uint8_t* dstBase, const int64_t* dstOff, const int32_t* targetLen,
+                                   int32_t* outLen, int32_t nBlocks, int32_t memKind, void* cudaStream,
+                                   int32_t device) {
+    GeneralArgs g{srcBase, srcOff, srcLen, dstBase, dstOff, targetLen, nullptr, nullptr, nullptr, outLen, nBlocks, true};
+    return run_general(g, memKind, cudaStream, device);
+}
+
+int32_t k4lz4_encode_x32(const uint8_t* src, int32_t srcLen, uint8_t* dst, int32_t dstCap, int32_t level) {
+    if (srcLen <= 0) return 0;
+    if (level >= 3) return K4LZ4_R_DELEGATE;
+    if (!src || (!dst && dstCap > 0)) return fail(K4LZ4_E_ARG, "null pointer argument");
+    if (dstCap <= 0) return -1;
+    int64_t so = 0, dof = 0; int32_t out = -1;
+    int rc = run(OP_ENCODE, src, &so, &srcLen, dst, &dof, &dstCap, &out, 1, level | k4::ENC_FLAG_X32, K4LZ4_MEM_HOST, nullptr, 0);
+    return rc != K4LZ4_OK ? rc : out;
+}
+
+int32_t k4lz4_encode_batch_x32(const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen,
+                               uint8_t* dstBase, const int64_t* dstOff, const int32_t* dstCap,
+                               int32_t* outLen, int32_t nBlocks, int32_t level, int32_t memKind,
+                               void* cudaStream, int32_t device) {
+    if (level < 0 || level > 0xFF) return fail(K4LZ4_E_ARG, "bad level");
+    return run(OP_ENCODE, srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, nBlocks, level | k4::ENC_FLAG_X32,
+               memKind, cudaStream, device);
+}
+
 int32_t k4lz4_encode_batch(const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen,
                            uint8_t* dstBase, const int64_t* dstOff, const int32_t* dstCap,
                            int32_t* outLen, int32_t nBlocks, int32_t level, int32_t memKind,
                            void* cudaStream, int32_t device) {
+    if (level < 0 || level > 0xFF) return fail(K4LZ4_E_ARG, "bad level");
     return run(OP_ENCODE, srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, nBlocks, level,
                memKind, cudaStream, device);
 }
@@ -536,6 +798,16 @@ int32_t k4lz4_pickle_batch(const uint8_t* srcBase, const int64_t* srcOff, const 
                memKind, cudaStream, device);
 }
 
+int32_t k4lz4_pickle_writer_bound(int32_t length) { return length <= 0 ? 0 : length + 1 + k4::pickle_diff_width(length); }
+
+int32_t k4lz4_pickle_writer_batch(const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen,
+                                  uint8_t* dstBase, const int64_t* dstOff, int32_t* outLen,
+                                  int32_t nMessages, int32_t level, int32_t memKind, void* cudaStream,
+                                  int32_t device) {
+    return run(OP_PICKLEW, srcBase, srcOff, srcLen, dstBase, dstOff, nullptr, outLen, nMessages, level,
+               memKind, cudaStream, device);
+}
+
 int32_t k4lz4_unpickled_size_batch(const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen,
                                    int32_t* outSize, int32_t nMessages, int32_t memKind,
                                    void* cudaStream, int32_t device) {
@@ -549,6 +821,45 @@ int32_t k4lz4_unpickle_batch(const uint8_t* srcBase, const int64_t* srcOff, cons
                              int32_t device) {
     return run(OP_UNPICKLE, srcBase, srcOff, srcLen, dstBase, dstOff, dstLen, outLen, nMessages, 0,
                memKind, cudaStream, device);
+}
+
+uint32_t k4lz4_xxh32(const uint8_t* data, int64_t length, uint32_t seed) {
+    return k4::xxh32_host(data, length > 0 && data ? (size_t)length : 0, seed);
+}
+
+int32_t k4lz4_xxh32_batch(const uint8_t* base, const int64_t* off, const int32_t* len, uint32_t seed,
+                          uint32_t* out, int32_t nBlocks, int32_t memKind, void* cudaStream, int32_t device) {
+    if (device_count_cached() <= 0) return fail(K4LZ4_E_NODEVICE, "no CUDA device available");
+    if (nBlocks < 0 || !base || !off || !len || !out) return fail(K4LZ4_E_ARG, "bad xxh32 arguments");
+    if (nBlocks == 0) return K4LZ4_OK;
+    DeviceGuard g(memKind == K4LZ4_MEM_HOST && device < 0 ? 0 : device);
+    if (!g.ok) return fail(K4LZ4_E_CUDA, "cudaSetDevice(%d) failed", device);
+    const unsigned ctas = (unsigned)(((int64_t)nBlocks * 4 + 127) / 128);
+    if (memKind == K4LZ4_MEM_DEVICE) {
+        k4::xxh32_batch_kernel<<<ctas, 128, 0, (cudaStream_t)cudaStream>>>(base, off, len, seed, out, nBlocks);
+        g_launches++;
+        CU_TRY(cudaGetLastError());
+        return K4LZ4_OK;
+    }
+    if (memKind != K4LZ4_MEM_HOST) return fail(K4LZ4_E_ARG, "unknown memKind %d", memKind);
+    // host memory: pack, one H2D, one kernel, one D2H (checksums are a side channel of the frame writer)
+    std::vector<int64_t> po((size_t)nBlocks);
+    int64_t tot = 0;
+    for (int i = 0; i < nBlocks; i++) { po[(size_t)i] = tot; tot += len[i] > 0 ? len[i] : 0; }
+    std::vector<uint8_t> pk((size_t)tot + 16);
+    for (int i = 0; i < nBlocks; i++) if (len[i] > 0) memcpy(pk.data() + po[(size_t)i], base + off[i], (size_t)len[i]);
+    DevMem dB, dM;
+    CU_TRY(dB.alloc((size_t)tot + 16));
+    CU_TRY(dM.alloc((size_t)nBlocks * 16));
+    int64_t* dOff = (int64_t*)dM.p; int32_t* dLen = (int32_t*)(dOff + nBlocks); uint32_t* dOut = (uint32_t*)(dLen + nBlocks);
+    CU_TRY(cudaMemcpy(dB.p, pk.data(), (size_t)tot, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(dOff, po.data(), (size_t)nBlocks * 8, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(dLen, len, (size_t)nBlocks * 4, cudaMemcpyHostToDevice));
+    k4::xxh32_batch_kernel<<<ctas, 128>>>((const uint8_t*)dB.p, dOff, dLen, seed, dOut, nBlocks);
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpy(out, dOut, (size_t)nBlocks * 4, cudaMemcpyDeviceToHost));
+    return K4LZ4_OK;
 }
 
 int32_t k4lz4_synth_host(uint8_t* base, int64_t nBlocks, int32_t blockSize, int32_t matchPermille,

@@ -20,7 +20,7 @@ namespace k4 {
 
 constexpr int R_CORRUPT = -1000;   // K4LZ4_R_CORRUPT
 
-__device__ __forceinline__ int pickle_diff_width(int v) {      // EffectiveSizeOf, pickle.cs:224-225
+__host__ __device__ __forceinline__ int pickle_diff_width(int v) {      // EffectiveSizeOf, pickle.cs:224-225
     return (v > 0xffff || v < 0) ? 4 : (v > 0xff ? 2 : 1);
 }
 
@@ -34,6 +34,32 @@ __device__ __forceinline__ void warp_shift_up(uint8_t* p, int len, int d, int la
         if (i < len) p[i + d] = v;
         __syncwarp();
     }
+}
+
+// LZ4Pickler.Pickle<TBufferWriter> (pickle.cs:113-148): the header width is fixed from the full
+// length before encoding (:129,161-165) and the payload is encoded in place with capacity n (:130-133).
+__device__ int pickle_writer_message_warp(const uint8_t* __restrict__ src, int n, uint8_t* __restrict__ dst,
+                                          int level, void* table) {
+    const int lane = lane_id();
+    if (n <= 0) return 0;                                        // :122
+    if (level >= 3) return -2;
+    const int k = pickle_diff_width(n);
+    const int hs = 1 + k;
+    int enc = (n < LIMIT_64K)
+        ? encode_spec_warp<false>(src, nullptr, (uint32_t)n, dst + hs, n, n - 1, reinterpret_cast<uint16_t*>(table))
+        : encode_block_warp(src, n, dst + hs, n, n - 1, table, false);
+    __syncwarp();
+    if (enc <= 0 || enc >= n) {                                  // :135-140
+        if (lane == 0) dst[0] = 0;
+        for (int i = lane; i < n; i += 32) dst[1 + i] = __ldg(src + i);
+        return 1 + n;
+    }
+    if (lane == 0) {
+        const int diff = n - enc;
+        dst[0] = (uint8_t)(((k == 4 ? 3 : k) & 3) << 6);
+        for (int i = 0; i < k; i++) dst[1 + i] = (uint8_t)((uint32_t)diff >> (8 * i));
+    }
+    return hs + enc;                                             // :146
 }
 
 __device__ int pickle_message_warp(const uint8_t* __restrict__ src, int n, uint8_t* __restrict__ dst,
@@ -96,13 +122,14 @@ __global__ void __launch_bounds__(ENC_WARPS_PER_CTA * 32)
 pickle_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restrict__ srcOff,
               const int32_t* __restrict__ srcLen, uint8_t* __restrict__ dstBase,
               const int64_t* __restrict__ dstOff, int32_t* __restrict__ outLen,
-              int nMessages, int level) {
+              int nMessages, int level, int writerVariant) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int wInCta = threadIdx.x >> 5;
     const int b = blockIdx.x * ENC_WARPS_PER_CTA + wInCta;
     if (b >= nMessages) return;
-    int r = pickle_message_warp(srcBase + srcOff[b], srcLen[b], dstBase + dstOff[b], level,
-                                smem + wInCta * ENC_TABLE_BYTES);
+    int r = writerVariant
+        ? pickle_writer_message_warp(srcBase + srcOff[b], srcLen[b], dstBase + dstOff[b], level, smem + wInCta * ENC_SLOT_BYTES)
+        : pickle_message_warp(srcBase + srcOff[b], srcLen[b], dstBase + dstOff[b], level, smem + wInCta * ENC_SLOT_BYTES);
     if (lane_id() == 0) outLen[b] = r;
 }
 

@@ -9,7 +9,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import _native as N
-from .batch import pickle_batch_host, unpickle_batch_host, unpickled_size_batch_host
+from .batch import pickle_batch_host, pickle_writer_batch_host, unpickle_batch_host, unpickled_size_batch_host
 from .codec import LZ4Level, DelegateToManagedEngine, _ro, _rw
 
 
@@ -28,6 +28,24 @@ class LZ4Pickler:
         if lens[0] == N.R_DELEGATE:
             raise DelegateToManagedEngine(f"level {int(level)} is not on the accelerated path")
         return out[0]
+
+    @staticmethod
+    def PickleTo(source, writer, level: LZ4Level = LZ4Level.L00_FAST) -> None:
+        """Pickle<TBufferWriter>(source, writer, level) -- LZ4Pickler.pickle.cs:113-148.  `writer` is
+        anything with write(bytes) (or a bytearray, which is extended): the IBufferWriter mirror.
+        NOTE the bytes differ from Pickle(): pessimistic header width, capacity-n encode."""
+        if writer is None:
+            raise ValueError("writer: cannot be null")                    # ArgumentNullException, :118-119
+        src = _ro(source)
+        if src.shape[0] == 0:
+            return
+        out, lens = pickle_writer_batch_host([src], level=int(level))
+        if lens[0] == N.R_DELEGATE:
+            raise DelegateToManagedEngine(f"level {int(level)} is not on the accelerated path")
+        if isinstance(writer, bytearray):
+            writer.extend(out[0])
+        else:
+            writer.write(out[0])
 
     @staticmethod
     def UnpickledSize(source) -> int:

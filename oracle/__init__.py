@@ -92,6 +92,8 @@ class Port(_Harness):
         lib.k4o_decompress_safe.argtypes = [_u8p, C.c_int, _u8p, C.c_int]
         lib.k4o_codec_encode.argtypes = [_u8p, C.c_int, _u8p, C.c_int, C.c_int, C.c_int]
         lib.k4o_codec_decode.argtypes = [_u8p, C.c_int, _u8p, C.c_int]
+        lib.k4o_codec_decode_dict.argtypes = [_u8p, C.c_int, _u8p, C.c_int, _u8p, C.c_int]
+        lib.k4o_codec_partial_decode.argtypes = [_u8p, C.c_int, _u8p, C.c_int]
         lib.k4o_pickle.argtypes = [_u8p, C.c_int, _u8p, _u8p, C.c_int]
         lib.k4o_unpickled_size.argtypes = [_u8p, C.c_int]
         lib.k4o_unpickle.argtypes = [_u8p, C.c_int, _u8p, C.c_int]
@@ -116,6 +118,21 @@ class Port(_Harness):
         r = int(self._lib.k4o_codec_decode(_ptr(s), int(s.shape[0]), _ptr(d), cap))
         return r, (d[:r].tobytes() if r > 0 else b"")
 
+    def decode_dict(self, src, cap: int, dictionary):
+        """LZ4Codec.Decode(src, dst, dict) semantics (LZ4Codec.cs:144-157) -> (ret, bytes)."""
+        s = _as_u8(src)
+        dd = _as_u8(dictionary)
+        d = np.zeros(max(cap, 1), dtype=np.uint8)
+        r = int(self._lib.k4o_codec_decode_dict(_ptr(s), int(s.shape[0]), _ptr(d), cap, _ptr(dd), int(dd.shape[0])))
+        return r, (d[:r].tobytes() if r > 0 else b"")
+
+    def partial_decode(self, src, target: int):
+        """LZ4Codec.PartialDecode semantics (LZ4Codec.cs:123-134) -> (ret, bytes)."""
+        s = _as_u8(src)
+        d = np.zeros(max(target, 1), dtype=np.uint8)
+        r = int(self._lib.k4o_codec_partial_decode(_ptr(s), int(s.shape[0]), _ptr(d), target))
+        return r, (d[:r].tobytes() if r > 0 else b"")
+
     def decompress_safe_raw(self, src, cap: int) -> int:
         """Engine-level return value (negative error position), LL64.dec.cs:465."""
         s = _as_u8(src)
@@ -130,6 +147,17 @@ class Port(_Harness):
         d = np.zeros(n + 1, dtype=np.uint8)
         scratch = np.zeros(max(n, 1024), dtype=np.uint8)
         r = int(self._lib.k4o_pickle(_ptr(s), n, _ptr(d), _ptr(scratch), level))
+        return d[:r].tobytes()
+
+    def pickle_writer(self, src, level: int = 0) -> bytes:
+        """LZ4Pickler.Pickle<TBufferWriter> (LZ4Pickler.pickle.cs:113-148): bytes advanced in the writer."""
+        s = _as_u8(src)
+        n = int(s.shape[0])
+        if n == 0:
+            return b""
+        self._lib.k4o_pickle_writer.argtypes = [_u8p, C.c_int, _u8p, C.c_int]
+        d = np.zeros(int(self._lib.k4o_pickle_writer_bound(n)), dtype=np.uint8)
+        r = int(self._lib.k4o_pickle_writer(_ptr(s), n, _ptr(d), level))
         return d[:r].tobytes()
 
     def unpickled_size(self, src) -> int:
@@ -162,6 +190,8 @@ class Ref(_Harness):
         super().__init__(lib)
         lib.k4ref_compress_fast.argtypes = [_u8p, C.c_int, _u8p, C.c_int]
         lib.k4ref_decompress_safe.argtypes = [_u8p, C.c_int, _u8p, C.c_int]
+        lib.k4ref_decompress_safe_usingDict.argtypes = [_u8p, C.c_int, _u8p, C.c_int, _u8p, C.c_int]
+        lib.k4ref_decompress_safe_partial.argtypes = [_u8p, C.c_int, _u8p, C.c_int]
 
     def version(self) -> int:
         return int(self._lib.k4ref_version())
@@ -187,6 +217,81 @@ class Ref(_Harness):
         r = int(self._lib.k4ref_decompress_safe(_ptr(s), n, _ptr(d), cap))
         r = -1 if r <= 0 else r
         return r, (d[:r].tobytes() if r > 0 else b"")
+
+
+def _ref_decode_dict(self, src, cap: int, dictionary):
+    s = _as_u8(src)
+    n = int(s.shape[0])
+    if n <= 0:
+        return 0, b""
+    dd = _as_u8(dictionary)
+    d = np.zeros(max(cap, 1), dtype=np.uint8)
+    r = int(self._lib.k4ref_decompress_safe_usingDict(_ptr(s), n, _ptr(d), cap, _ptr(dd), int(dd.shape[0])))
+    r = -1 if r <= 0 else r
+    return r, (d[:r].tobytes() if r > 0 else b"")
+
+
+def _ref_partial_decode(self, src, target: int):
+    s = _as_u8(src)
+    n = int(s.shape[0])
+    if n <= 0:
+        return 0, b""
+    d = np.zeros(max(target, 1), dtype=np.uint8)
+    r = int(self._lib.k4ref_decompress_safe_partial(_ptr(s), n, _ptr(d), target))
+    r = -1 if r <= 0 else r
+    return r, (d[:r].tobytes() if r > 0 else b"")
+
+
+Ref.decode_dict = _ref_decode_dict
+Ref.partial_decode = _ref_partial_decode
+
+
+def _ref_xxh32(self, data, seed: int = 0) -> int:
+    s = _as_u8(data)
+    self._lib.k4ref_xxh32.restype = C.c_uint32
+    self._lib.k4ref_xxh32.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32]
+    return int(self._lib.k4ref_xxh32(s.ctypes.data, int(s.shape[0]), seed))
+
+
+def _ref_frame_compress(self, data, block_checksum: bool = False, content_checksum: bool = False) -> bytes:
+    """upstream LZ4F_compressFrame: independent 64 KiB blocks, acceleration 1 (orig/lib/lz4frame.c)."""
+    s = _as_u8(data)
+    L = self._lib
+    L.k4ref_frame_bound.restype = C.c_size_t; L.k4ref_frame_bound.argtypes = [C.c_size_t]
+    L.k4ref_frame_compress.restype = C.c_size_t
+    L.k4ref_frame_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+    cap = int(L.k4ref_frame_bound(int(s.shape[0])))
+    d = np.zeros(cap, dtype=np.uint8)
+    r = int(L.k4ref_frame_compress(s.ctypes.data, int(s.shape[0]), d.ctypes.data, cap, int(block_checksum), int(content_checksum)))
+    if r == 0:
+        raise RuntimeError("LZ4F_compressFrame failed")
+    return d[:r].tobytes()
+
+
+def _ref_frame_decompress(self, frame, cap: int):
+    """upstream LZ4F_decompress over a whole frame -> bytes, or None on any error."""
+    s = _as_u8(frame)
+    L = self._lib
+    L.k4ref_frame_decompress.restype = C.c_size_t
+    L.k4ref_frame_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    d = np.zeros(max(cap, 1), dtype=np.uint8)
+    r = int(L.k4ref_frame_decompress(s.ctypes.data, int(s.shape[0]), d.ctypes.data, cap))
+    return None if r == (1 << 64) - 1 else d[:r].tobytes()
+
+
+Ref.xxh32 = _ref_xxh32
+Ref.frame_compress = _ref_frame_compress
+Ref.frame_decompress = _ref_frame_decompress
+
+
+def _port_xxh32(self, data, seed: int = 0) -> int:
+    s = _as_u8(data)
+    self._lib.k4o_xxh32.restype = C.c_uint32
+    self._lib.k4o_xxh32.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32]
+    return int(self._lib.k4o_xxh32(s.ctypes.data, int(s.shape[0]), seed))
+
+
+Port.xxh32 = _port_xxh32
 
 
 def have_ref() -> bool:

@@ -299,6 +299,164 @@ output_error:
     return (int)(-ip) - 1;                                             /* :465 */
 }
 
+/*
+ * The general form of the same loop: LZ4_decompress_generic with endOnInputSize and
+ *   - an external dictionary (usingExtDict, lowPrefix = dst): LZ4_decompress_safe_forceExtDict,
+ *     Engine/x64/LL64.dec.cs:510-521, reached from LZ4_decompress_safe_usingDict :523-546.  The
+ *     prefix variants of :529-541 (dictionary adjacent to dst) read the same bytes through plain
+ *     pointers and reject the same offsets (match + dictSize < lowPrefix, :338), so one
+ *     restatement covers all three; a dictionary of >= 64 KiB switches the offset test off
+ *     (checkOffset, :147) -- every 16-bit offset then lands inside it.
+ *   - earlyEnd = partial: LZ4_decompress_safe_partial :548-556 (LLxx.cs:29-39 passes
+ *     targetOutputSize == dstCapacity == the target length), paths :256-280, :301-307, :387-406.
+ * Ext-dict matches follow :341-378 (own length test, then dictionary part + block part); their
+ * bytes are those of the virtual window [dict | dst].
+ */
+static int decompress_general(const uint8_t *src, int n, uint8_t *dst, int outputSize, int partial,
+                              const uint8_t *dict, int dictSize)
+{
+    if (src == NULL) return -1;                                        /* :136 */
+    int64_t ip = 0, op = 0;
+    const int64_t iend = n, oend = outputSize;
+    const int64_t shortiend = iend - 14 - 2, shortoend = oend - 14 - 18;
+    const int checkOffset = dictSize < 65536;                          /* :147 */
+    const int extDict = dict != NULL && dictSize > 0;
+
+    if (outputSize == 0) {                                             /* :162-168 */
+        if (partial) return 0;
+        return (n == 1 && src[0] == 0) ? 0 : -1;
+    }
+    if (n == 0) return -1;                                             /* :172 */
+
+    for (;;) {
+        uint32_t token = src[ip++];
+        int64_t length = token >> 4;
+        int64_t offset, match, cpy;
+
+        if (length != 15 && ip < shortiend && op <= shortoend) {       /* :191-193 */
+            memcpy(dst + op, src + ip, (size_t)length);
+            op += length; ip += length;
+            length = token & 15;
+            offset = src[ip] | (src[ip + 1] << 8); ip += 2;
+            match = op - offset;
+            if (length != 15 && offset >= 8 && match >= 0) {           /* :211-213 (match >= lowPrefix) */
+                length += K_MINMATCH;
+                for (int64_t i = 0; i < length; i++) dst[op + i] = dst[match + i];
+                op += length;
+                continue;
+            }
+            goto copy_match;
+        }
+
+        if (length == 15) {                                            /* :228-243 */
+            if (ip >= iend - 15) goto output_error;
+            for (;;) {
+                uint32_t s = src[ip++];
+                length += s;
+                if (ip >= iend - 15) break;
+                if (s != 255) break;
+            }
+        }
+
+        cpy = op + length;                                             /* :246 */
+        if (cpy > oend - K_MFLIMIT || ip + length > iend - (2 + 1 + K_LASTLITERALS)) {
+            if (partial) {                                             /* :256-280 */
+                if (ip + length > iend - (2 + 1 + K_LASTLITERALS) && ip + length != iend) goto output_error;
+                if (cpy > oend) { cpy = oend; length = oend - op; }
+            } else {
+                if (ip + length != iend || cpy > oend) goto output_error;   /* :291-294 */
+            }
+            memmove(dst + op, src + ip, (size_t)length);               /* :297 */
+            ip += length; op += length;
+            if (!partial || cpy == oend || ip == iend) break;          /* :304-307 */
+        } else {
+            memcpy(dst + op, src + ip, (size_t)length);                /* :311 */
+            ip += length; op = cpy;
+        }
+
+        offset = src[ip] | (src[ip + 1] << 8); ip += 2;                /* :318-320 */
+        match = op - offset;
+        length = token & 15;
+
+    copy_match:
+        if (length == 15) {                                            /* :326-334 */
+            for (;;) {
+                uint32_t s = src[ip++];
+                length += s;
+                if (ip >= iend - K_LASTLITERALS + 1) goto output_error;
+                if (s != 255) break;
+            }
+        }
+        length += K_MINMATCH;                                          /* :336 */
+        if (checkOffset && match + dictSize < 0) goto output_error;    /* :338 */
+
+        if (extDict && match < 0) {                                    /* :341-378 */
+            if (op + length > oend - K_LASTLITERALS) {
+                if (partial) length = (oend - op) < length ? (oend - op) : length;
+                else goto output_error;
+            }
+            for (int64_t i = 0; i < length; i++) {                     /* bytes of the window [dict | dst] */
+                const int64_t j = match + i;
+                dst[op + i] = j < 0 ? dict[dictSize + j] : dst[j];
+            }
+            op += length;
+            continue;
+        }
+        if (match < 0) {
+            /* no dictionary memory behind dst (checkOffset off can only happen with a dictionary):
+             * the reference would read foreign memory; unreachable through LZ4Codec */
+            goto output_error;
+        }
+
+        cpy = op + length;                                             /* :383 */
+        if (partial && cpy > oend - 12) {                              /* :387-406 */
+            const int64_t mlen = length < oend - op ? length : oend - op;
+            for (int64_t i = 0; i < mlen; i++) dst[op + i] = offset ? dst[match + i] : 0;
+            op += mlen;
+            if (op == oend) break;
+            continue;
+        }
+        if (cpy > oend - 12 && cpy > oend - K_LASTLITERALS) goto output_error;   /* :427-433 */
+        if (offset == 0) memset(dst + op, 0, (size_t)length);
+        else for (int64_t i = 0; i < length; i++) dst[op + i] = dst[match + i];
+        op = cpy;                                                      /* :450 */
+    }
+    return (int)op;                                                    /* :454-457 */
+
+output_error:
+    return (int)(-ip) - 1;                                             /* :465 */
+}
+
+/* LZ4_decompress_safe_usingDict -- Engine/x64/LL64.dec.cs:523-546 */
+int k4o_decompress_safe_usingDict(const uint8_t *src, int n, uint8_t *dst, int cap,
+                                  const uint8_t *dict, int dictSize)
+{
+    if (dictSize == 0 || dict == NULL) return k4o_decompress_safe(src, n, dst, cap);
+    return decompress_general(src, n, dst, cap, 0, dict, dictSize);
+}
+
+/* LZ4_decompress_safe_partial as called by LLxx.cs:29-39 (dstCapacity == targetOutputSize) */
+int k4o_decompress_safe_partial(const uint8_t *src, int n, uint8_t *dst, int target)
+{
+    return decompress_general(src, n, dst, target, 1, NULL, 0);
+}
+
+/* LZ4Codec.Decode(byte*,int,byte*,int,byte*,int) -- LZ4Codec.cs:144-157 */
+int k4o_codec_decode_dict(const uint8_t *src, int n, uint8_t *dst, int cap, const uint8_t *dict, int dictSize)
+{
+    if (n <= 0) return 0;
+    int r = k4o_decompress_safe_usingDict(src, n, dst, cap, dict, dictSize);
+    return r <= 0 ? -1 : r;
+}
+
+/* LZ4Codec.PartialDecode(byte*,int,byte*,int) -- LZ4Codec.cs:123-134 */
+int k4o_codec_partial_decode(const uint8_t *src, int n, uint8_t *dst, int target)
+{
+    if (n <= 0) return 0;
+    int r = k4o_decompress_safe_partial(src, n, dst, target);
+    return r <= 0 ? -1 : r;
+}
+
 /* LZ4Codec.Encode(byte*,int,byte*,int,LZ4Level) -- LZ4Codec.cs:40-52.
  * level >= 3 (HC) is outside the hot path: -2 tells the caller to delegate. */
 int k4o_codec_encode(const uint8_t *src, int n, uint8_t *dst, int cap, int level, int enforce32)
@@ -349,6 +507,31 @@ int k4o_pickle(const uint8_t *src, int n, uint8_t *dst, uint8_t *scratch, int le
 }
 
 /*
+ * LZ4Pickler.Pickle<TBufferWriter>(source, writer, level) -- LZ4Pickler.pickle.cs:113-148.
+ * Differs from the byte[] variant in two ways that change the bytes: the header width is fixed
+ * BEFORE encoding from the full length (GetPessimisticHeaderSize, :129,161-165), and the payload
+ * is encoded straight into the writer's span with capacity n (:130-133), not into the 1024-byte
+ * minimum scratch.  `dst` must hold k4o_pickle_writer_bound(n) bytes.  Returns bytes advanced.
+ */
+int k4o_pickle_writer_bound(int n) { return n <= 0 ? 0 : 1 + size_of_diff(n) + n; }
+
+int k4o_pickle_writer(const uint8_t *src, int n, uint8_t *dst, int level)
+{
+    if (n == 0) return 0;                                              /* :122 */
+    const int headerSize = 1 + size_of_diff(n);                        /* :129 */
+    int enc = k4o_codec_encode(src, n, dst + headerSize, n, level, 0); /* :132-133 */
+    if (enc <= 0 || enc >= n) {                                        /* :135-140 */
+        dst[0] = 0;
+        memmove(dst + 1, src, (size_t)n);
+        return 1 + n;
+    }
+    const int diff = n - enc, k = headerSize - 1;                      /* :203-212 with the pessimistic width */
+    dst[0] = (uint8_t)(((k == 4 ? 3 : k) & 3) << 6);
+    for (int i = 0; i < k; i++) dst[1 + i] = (uint8_t)((uint32_t)diff >> (8 * i));
+    return headerSize + enc;                                           /* :146 */
+}
+
+/*
  * DecodeHeaderV0 + UnpickledSize -- LZ4Pickler.unpickle.cs:131-158,83-92.
  * Returns the unpickled size, or K4O_PICKLE_CORRUPT where the reference throws
  * InvalidDataException (bad version :131-135, truncated header :142-143,153).
@@ -388,4 +571,34 @@ int k4o_unpickle(const uint8_t *src, int n, uint8_t *dst, int dstLen)
     int dec = k4o_codec_decode(src + 1 + k, n - 1 - k, dst, dstLen);   /* :125 */
     if (dec != expected) return K4O_PICKLE_CORRUPT;                    /* :126-128 */
     return expected;
+}
+
+/* ---- XXH32 (LZ4 Frame checksums) --------------------------------------------------------------
+ * Restates /root/reference/orig/lib/xxhash.c:263-390 (XXH32_round, XXH32_avalanche, XXH32_finalize,
+ * XXH32_endian_align); the reference consumes it through NuGet K4os.Hash.xxHash
+ * (Streams/Frames/LZ4FrameWriter.cs:162-181, LZ4FrameReader.cs:114-134). */
+static inline uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+
+uint32_t k4o_xxh32(const uint8_t *p, size_t len, uint32_t seed)
+{
+    const uint32_t P1 = 2654435761u, P2 = 2246822519u, P3 = 3266489917u, P4 = 668265263u, P5 = 374761393u;
+    size_t i = 0;
+    uint32_t h;
+    if (len >= 16) {
+        uint32_t v1 = seed + P1 + P2, v2 = seed + P2, v3 = seed, v4 = seed - P1;
+        for (; i + 16 <= len; i += 16) {
+            v1 = rotl32(v1 + rd32(p + i) * P2, 13) * P1;
+            v2 = rotl32(v2 + rd32(p + i + 4) * P2, 13) * P1;
+            v3 = rotl32(v3 + rd32(p + i + 8) * P2, 13) * P1;
+            v4 = rotl32(v4 + rd32(p + i + 12) * P2, 13) * P1;
+        }
+        h = rotl32(v1, 1) + rotl32(v2, 7) + rotl32(v3, 12) + rotl32(v4, 18);
+    } else {
+        h = seed + P5;
+    }
+    h += (uint32_t)len;
+    for (; i + 4 <= len; i += 4) h = rotl32(h + rd32(p + i) * P3, 17) * P4;
+    for (; i < len; i++) h = rotl32(h + p[i] * P5, 11) * P1;
+    h ^= h >> 15; h *= P2; h ^= h >> 13; h *= P3; h ^= h >> 16;
+    return h;
 }

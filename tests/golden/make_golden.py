@@ -5,7 +5,8 @@
 1. issue64_block0.{lz4,bin}: the reference's own golden DECODE vector -- block #0 of
    /root/reference/assets/issue64/input.dat (a "bv41" container: 12-byte header at byte 20,
    14 505 compressed bytes -> 65 536 bytes == output.dat[0:65536]); exercised by the
-   reference's Issue64.cs:16-55.
+   reference's Issue64.cs:16-55.  issue64_block1.{lz4,bin}: block #1 of the same file (366 -> 3 034
+   bytes), which only decodes with block #0's output as external dictionary.
 2. encode_rows.json: known-answer rows for LZ4Codec.Encode at L00_FAST in the style of the
    reference's ChecksumBlockTests.cs:185-216 (exact length, Adler-32 of the compressed bytes,
    first 60 compressed bytes base64) over the deterministic inputs of tests/inputs.py,
@@ -44,6 +45,16 @@ def main():
     assert r == usize == 65536 and out == expect[:usize]
     open(os.path.join(HERE, "issue64_block0.lz4"), "wb").write(comp)
     open(os.path.join(HERE, "issue64_block0.bin"), "wb").write(expect[:usize])
+    # block #1 needs block #0's output as its dictionary (Issue64.cs:39-49)
+    pos1 = 32 + csize
+    assert blob[pos1:pos1 + 4] == b"bv41"
+    usize1, csize1 = struct.unpack("<II", blob[pos1 + 4:pos1 + 12])
+    comp1 = blob[pos1 + 12:pos1 + 12 + csize1]
+    r1, out1 = R.decode_dict(comp1, usize1, expect[:usize])
+    assert r1 == usize1 == 3034 and csize1 == 366 and out1 == expect[usize:usize + usize1]
+    assert blob[pos1 + 12 + csize1:pos1 + 16 + csize1] == b"bv4$"
+    open(os.path.join(HERE, "issue64_block1.lz4"), "wb").write(comp1)
+    open(os.path.join(HERE, "issue64_block1.bin"), "wb").write(out1)
 
     # 2. encode rows
     rows = []

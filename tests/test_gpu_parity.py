@@ -184,7 +184,7 @@ def test_device_path_batch_roundtrip_and_host_generator(k4):
     torch.cuda.synchronize()
     assert torch.equal(out, raw) and bool((olen == bs).all())
     c, l = comp.cpu().numpy(), clen.cpu().numpy()
-    for i in range(0, nb, 7):
+    for i in range(nb):                                      # every block, not a sample
         r, ref = chk.encode(host[i * bs:(i + 1) * bs])
         assert r == int(l[i]) and c[i * bound:i * bound + r].tobytes() == ref
         assert (c[i * bound + r:(i + 1) * bound] == 0xCD).all()      # slot tail untouched
@@ -305,3 +305,296 @@ def test_pickler_batch_at_scale_property(k4):
     h_raw, h_pk, h_pl = raw[:int(off[64])].cpu().numpy(), pk[:int(poff[64])].cpu().numpy(), plen[:64].cpu().numpy()
     for i in range(64):
         assert h_pk[poff[i]:poff[i] + h_pl[i]].tobytes() == port.pickle(h_raw[off[i]:off[i] + sizes[i]].tobytes()), i
+
+
+def test_datagen_blocks_encode_and_decode_gpu(k4, chk):
+    """The workload the survey names (RDG_genBuffer 0.63 / 0.55): every block encoded by the GPU is
+    byte-identical to the reference engine's output, decodes back, and stays on the tile path."""
+    import oracle
+    port = oracle.Port()
+    bs, nb = 65536, 192
+    for mp in (0.63, 0.55):
+        raw = port.datagen(nb * bs, mp, 0.0, 1234)
+        blocks = [raw[i * bs:(i + 1) * bs].tobytes() for i in range(nb)]
+        enc, lens = k4.batch.encode_batch_host(blocks)
+        for i, b in enumerate(blocks):
+            assert (int(lens[i]), enc[i]) == chk.encode(b), (mp, i)
+        k4.batch.decode_stats(0, reset=True)
+        dec, dl = k4.batch.decode_batch_host(enc, [bs] * nb)
+        st = k4.batch.decode_stats(0, reset=True)
+        assert dec == blocks and dl.tolist() == [bs] * nb
+        assert st["tile"] == nb and st["generic"] == 0, st       # clean data never needs the exact fallback
+
+
+def test_issue64_block0_reencoded_by_gpu(k4, chk):
+    expect = open(os.path.join(G, "issue64_block0.bin"), "rb").read()
+    enc, lens = k4.batch.encode_batch_host([expect])
+    assert (int(lens[0]), enc[0]) == chk.encode(expect)
+    out = bytearray(65536)
+    assert k4.LZ4Codec.Decode(enc[0], out) == 65536 and bytes(out) == expect
+
+
+def test_tile_path_with_oversized_capacity(k4):
+    """dstCap > 64 KiB while the decoded size is <= 64 KiB must stay on the tile path and leave the
+    slack untouched (BlockRoundtripTests.cs:44-61 decodes into a 2x buffer)."""
+    import oracle
+    port = oracle.Port()
+    datas = [inputs.gen(k, n, 3) for k in ("text2", "synth525", "lorem", "runs") for n in (65536, 40000, 1000)]
+    enc = [port.encode(d)[1] for d in datas]
+    k4.batch.decode_stats(0, reset=True)
+    caps = [200000, 65537, 131072] * 4
+    dec, dl = k4.batch.decode_batch_host(enc, caps)
+    st = k4.batch.decode_stats(0, reset=True)
+    assert dec == datas and dl.tolist() == [len(d) for d in datas]
+    assert st["tile"] + st["tile_big"] == len(datas), st
+    big = bytearray(b"\xCD" * 200000)
+    assert k4.LZ4Codec.Decode(enc[0], big) == 65536 and bytes(big[65536:]) == b"\xCD" * (200000 - 65536)
+
+
+def test_decode_paths_cover_every_engine(k4):
+    """Incompressible blocks (compressed size > 65535 / > the small stage), a block of more than
+    16384 sequences and a multi-megabyte length-byte run all take their designated engine and agree
+    with the oracle."""
+    import oracle
+    port = oracle.Port()
+    rnd = inputs.gen("random", 65536, 1)                                   # -> 65 794 compressed bytes: generic
+    mid = inputs.gen("random", 45000, 2) + inputs.gen("repeat", 20536, 7)  # ~45 KB compressed: big stage
+    streams = [port.encode(rnd)[1], port.encode(mid)[1]]
+    caps = [65536, 65536]
+    # 5 MB of 0xFF length bytes (ADVICE round 1: 32-bit length overflow): must be rejected, not crash
+    streams.append(b"\xF0" + b"\xFF" * (5 << 20) + b"\x00")
+    caps.append(65536)
+    streams.append(b"\x0F" + b"\x01\x00" + b"\xFF" * (9 << 20) + b"\x00" + b"\x50abcde")
+    caps.append(65536)
+    k4.batch.decode_stats(0, reset=True)
+    dec, dl = k4.batch.decode_batch_host(streams, caps)
+    st = k4.batch.decode_stats(0, reset=True)
+    for i, (c, cap) in enumerate(zip(streams, caps)):
+        r, ref = port.decode(c, cap)
+        assert int(dl[i]) == r, (i, int(dl[i]), r)
+        if r > 0:
+            assert dec[i] == ref
+    assert st["generic"] >= 3 and st["tile_big"] == 1, st
+
+
+def test_dictionary_decode_gpu(k4):
+    """LZ4Codec.Decode(source, target, dictionary) (LZ4Codec.cs:144-157): the reference's second
+    golden vector, then mutated streams against the restatement of LL64.dec.cs:338-378."""
+    import oracle
+    port = oracle.Port()
+    comp = open(os.path.join(G, "issue64_block1.lz4"), "rb").read()
+    expect = open(os.path.join(G, "issue64_block1.bin"), "rb").read()
+    dic = open(os.path.join(G, "issue64_block0.bin"), "rb").read()
+    out = bytearray(b"\xCD" * 4000)
+    assert k4.LZ4Codec.Decode(comp, out, dic) == 3034 and bytes(out[:3034]) == expect
+    assert bytes(out[3034:]) == b"\xCD" * (4000 - 3034)
+    assert k4.LZ4Codec.Decode(comp, bytearray(3034)) == -1                 # without the dictionary
+    assert k4.LZ4Codec.Decode(comp, 0, len(comp), out, 0, 3034, dic, 0, len(dic)) == 3034
+    rng = np.random.default_rng(21)
+    streams, caps, dicts = [], [], []
+    for it in range(1500):
+        n = int(rng.choice([40, 200, 1000, 5000]))
+        c = bytearray(port.encode(inputs.gen(["text2", "lowent", "runs", "lorem", "random"][it % 5], n, it))[1])
+        if it % 3 and len(c) > 8:
+            for _ in range(3):
+                c[int(rng.integers(1, len(c) - 2))] = int(rng.integers(0, 256))
+        streams.append(bytes(c)); caps.append(int(rng.choice([n, n + 9, n - 1, 2 * n])))
+        dicts.append(inputs.gen("text2", int(rng.choice([0, 1, 7, 64, 300, 4096, 70000])), it + 1))
+    dec, got = k4.batch.decode_dict_batch_host(streams, caps, dicts)
+    for i in range(len(streams)):
+        r, ref = port.decode_dict(streams[i], caps[i], dicts[i]) if dicts[i] else port.decode(streams[i], caps[i])
+        assert int(got[i]) == r, (i, int(got[i]), r)
+        if r > 0 and not inputs.uses_zero_offset(streams[i]):
+            assert dec[i] == ref, i
+
+
+def test_partial_decode_gpu(k4):
+    """LZ4Codec.PartialDecode (LZ4Codec.cs:123-134; PartialDecompressionTests.cs:10-46)."""
+    import oracle
+    port = oracle.Port()
+    for size, num in [(127, 127), (128, 128), (256, 256), (512, 17), (511, 13), (511, 31)]:
+        src = inputs.gen("lorem", size, 0)
+        enc = bytearray(k4.LZ4Codec.MaximumOutputSize(size))
+        n = k4.LZ4Codec.Encode(src, enc)
+        dec = bytearray(b"\xCD" * size)
+        assert k4.LZ4Codec.PartialDecode(bytes(enc[:n]), 0, n, dec, 0, num) == num
+        assert bytes(dec[:num]) == src[:num] and bytes(dec[num:]) == b"\xCD" * (size - num)
+    rng = np.random.default_rng(4)
+    streams, targets = [], []
+    for it in range(1500):
+        n = int(rng.choice([30, 100, 1000, 5000, 70000]))
+        c = port.encode(inputs.gen(["text2", "lowent", "runs", "lorem", "random"][it % 5], n, it))[1]
+        if it % 4 == 3:
+            c = inputs.mutate(c, rng)
+        streams.append(c)
+        targets.append(int(rng.choice([0, 1, 5, 12, 13, n // 3, n // 2, n - 1, n, n + 1, 2 * n])))
+    dec, got = k4.batch.partial_decode_batch_host(streams, targets)
+    for i in range(len(streams)):
+        r, ref = port.partial_decode(streams[i], targets[i])
+        assert int(got[i]) == r, (i, int(got[i]), r)
+        if r > 0 and not inputs.uses_zero_offset(streams[i]):
+            assert dec[i] == ref, i
+
+
+def test_block_encoder_decoder_batched_topup(k4):
+    """LZ4BlockEncoder / LZ4BlockDecoder with a batched top-up equal N single-block
+    reference calls (Encoders/LZ4EncoderBase.cs:47-87, LZ4BlockEncoder.cs:18-23, LZ4BlockDecoder.cs:39-55)."""
+    import oracle
+    port = oracle.Port()
+    bs = 65536
+    data = (inputs.gen("text2", 3 * bs, 1) + inputs.gen("random", bs, 2) + inputs.gen("synth525", 2 * bs, 3)
+            + inputs.gen("lorem", 5000, 4))                                   # last block is short
+    enc = k4.LZ4BlockEncoder(k4.LZ4Level.L00_FAST, bs, batch_blocks=16)
+    assert enc.BlockSize == bs
+    assert enc.TopupMany(data) == len(data) and enc.BlocksQueued == 7
+    got = enc.EncodeMany(allowCopy=True)
+    assert len(got) == 7 and enc.BlocksQueued == 0
+    blocks = [data[i:i + bs] for i in range(0, len(data), bs)]
+    for (n, payload), raw in zip(got, blocks):
+        r, ref = port.encode(raw)                                             # LZ4Codec.Encode per block
+        if r >= len(raw):
+            assert n == -len(raw) and payload == raw                          # allowCopy: stored raw
+        else:
+            assert (n, payload) == (r, ref)
+    assert got[3][0] == -bs                                                   # the random block did not compress
+    # allowCopy=False keeps the expanded stream
+    assert enc.TopupMany(blocks[3]) == bs
+    (n, payload), = enc.EncodeMany(allowCopy=False)
+    assert (n, payload) == port.encode(blocks[3])
+    # single-block interface (Topup / Encode) and the too-small-target error
+    assert enc.Topup(blocks[0][:1000]) == 1000 and enc.BytesReady == 1000
+    tgt = bytearray(k4.LZ4Codec.MaximumOutputSize(1000))
+    n = enc.Encode(tgt, allowCopy=True)
+    assert (n, bytes(tgt[:n])) == port.encode(blocks[0][:1000])
+    assert enc.Topup(blocks[3][:5000]) == 5000
+    with pytest.raises(RuntimeError):
+        enc.Encode(bytearray(100), allowCopy=True)
+    # decoder: one call for the whole list, raw blocks passed through, Drain/Peek on the last one
+    dec = k4.LZ4BlockDecoder(bs)
+    out = dec.DecodeMany([(p, n < 0) for n, p in got])
+    assert out == blocks
+    assert dec.BytesReady == len(blocks[-1])
+    tail = bytearray(10)
+    dec.Drain(tail, -10, 10)
+    assert bytes(tail) == blocks[-1][-10:]
+    assert dec.Decode(port.encode(blocks[0])[1]) == bs and bytes(dec.Peek(-bs)) == blocks[0]
+    with pytest.raises(RuntimeError):
+        dec.DecodeMany([b"\x1f\x00"])
+
+
+def test_pickle_writer_variant_matches_oracle(k4):
+    """Pickle<TBufferWriter> (LZ4Pickler.pickle.cs:113-148): pessimistic header, capacity-n encode --
+    different bytes than the byte[] variant for some inputs, same round trip."""
+    import oracle
+    port = oracle.Port()
+    rng = np.random.default_rng(8)
+    msgs = [b"x", inputs.gen("random", 300, 1), b"a" * 200, b"a" * 300, b"a" * 5000, b"a" * 70000, b"ab" * 40000]
+    for i in range(400):
+        n = int(rng.integers(1, 4097)) if i % 3 else int(rng.choice([255, 256, 257, 270, 1004, 1023, 1024, 1025, 4096]))
+        msgs.append(inputs.gen(["text2", "synth435", "lorem", "random", "lowent"][i % 5], n, i))
+    pk, lens = k4.batch.pickle_writer_batch_host(msgs)
+    differ = 0
+    for m, p in zip(msgs, pk):
+        assert p == port.pickle_writer(m), len(m)
+        assert k4.LZ4Pickler.Unpickle(p) == m if len(m) in (1, 200, 300, 70000) else True
+        differ += p != port.pickle(m)
+    assert differ > 0                       # the two variants are not byte-identical (SURVEY 8a P1')
+    un, ul = k4.batch.unpickle_batch_host(pk)
+    assert un == msgs
+    w = bytearray(b"head")
+    k4.LZ4Pickler.PickleTo(b"a" * 300, w)
+    assert bytes(w) == b"head" + port.pickle_writer(b"a" * 300)
+
+
+def test_enforce32_engine_gpu(k4):
+    """LL.Enforce32 (LL.tools.cs:29-36): the 32-bit engine differs from the 64-bit one only for inputs of
+    >= 65 547 bytes (hash4 instead of hash5 on the u32 table); both variants against the restatement."""
+    import ctypes as C
+    import oracle
+    port = oracle.Port()
+    L = k4._native.lib()
+    for n in (1000, 65546, 65547, 100000, 149130):
+        d = inputs.gen("text2", n, 3)
+        src = np.frombuffer(d, dtype=np.uint8)
+        cap = k4.LZ4Codec.MaximumOutputSize(n)
+        dst = np.zeros(cap, dtype=np.uint8)
+        r32 = int(L.k4lz4_encode_x32(src.ctypes.data, n, dst.ctypes.data, cap, 0))
+        assert (r32, dst[:r32].tobytes()) == port.encode(d, enforce32=True), n
+        r64 = int(L.k4lz4_encode(src.ctypes.data, n, dst.ctypes.data, cap, 0))
+        assert (r64, dst[:r64].tobytes()) == port.encode(d), n
+        out = bytearray(n)
+        assert k4.LZ4Codec.Decode(dst[:r64].tobytes(), out) == n and bytes(out) == d
+    a, b = port.encode(inputs.gen("text2", 149130, 3)), port.encode(inputs.gen("text2", 149130, 3), enforce32=True)
+    assert a != b                                    # the two engines really differ above the threshold
+
+
+def test_all_devices_split_uses_every_gpu(k4):
+    """K4LZ4_ALL_DEVICES on a box with >= 2 GPUs: one host-memory call, every GPU decodes its contiguous
+    slice (decode path counters per device), results identical to the single-device call.  Skipped on a
+    1-GPU lease; run with `gpurun --gpus 2` (log committed under profiles/)."""
+    from k4os.compression.lz4_b200 import _native as N
+    ndev = N.lib().k4lz4_device_count()
+    if ndev < 2:
+        pytest.skip("needs at least two GPUs")
+    import oracle
+    port = oracle.Port()
+    bs, nb = 65536, 64 * ndev
+    raw = port.datagen(nb * bs, 0.63, 0.0, 4321)
+    blocks = [raw[i * bs:(i + 1) * bs].tobytes() for i in range(nb)]
+    enc1, len1 = k4.batch.encode_batch_host(blocks, device=0)
+    encA, lenA = k4.batch.encode_batch_host(blocks, device=N.ALL_DEVICES)
+    assert encA == enc1 and lenA.tolist() == len1.tolist()
+    for d in range(ndev):
+        k4.batch.decode_stats(d, reset=True)
+    src, so, sl = k4.batch._pack(enc1)
+    caps = np.full(nb, bs, dtype=np.int32)
+    doff = np.arange(nb, dtype=np.int64) * bs
+    dst = np.zeros(nb * bs, dtype=np.uint8)
+    got = k4.batch.decode_batch_flat_host(src, so, sl, dst, doff, caps, device=N.ALL_DEVICES)
+    assert got.tolist() == [bs] * nb and dst.tobytes() == raw.tobytes()
+    per_dev = [k4.batch.decode_stats(d, reset=True)["tile"] for d in range(ndev)]
+    assert sum(per_dev) == nb and all(v > 0 for v in per_dev), per_dev
+
+
+def test_frame_container_interoperates_with_upstream(k4):
+    """LZ4 frames of independent blocks written by frame.write_frame decode with
+    upstream lz4frame.c, upstream's frames decode with frame.read_frame, checksums (GPU XXH32 per
+    block, host XXH32 for header / content) included; corruption is detected."""
+    import oracle
+    from k4os.compression.lz4_b200 import frame as F
+    if not oracle.have_ref():
+        pytest.skip("needs oracle/_ref (upstream lz4frame.c)")
+    ref = oracle.Ref()
+    port = oracle.Port()
+    rng = np.random.default_rng(6)
+    datas = [b"", b"a", inputs.gen("text2", 1000, 1), inputs.gen("synth525", 3 * 65536 + 777, 2),
+             inputs.gen("random", 65536 + 5, 3), port.datagen(5 * 65536, 0.63).tobytes()]
+    for d in datas:
+        a = np.frombuffer(d, dtype=np.uint8)
+        assert F.xxh32(d, 7) == port.xxh32(a, 7)
+        for bc in (False, True):
+            for cc in (False, True):
+                mine = F.write_frame(d, 65536, bc, cc)
+                assert ref.frame_decompress(mine, len(d) + 16) == d, (len(d), bc, cc)
+                assert F.read_frame(mine) == d
+                theirs = ref.frame_compress(d, bc, cc)
+                assert F.read_frame(theirs) == d, (len(d), bc, cc)
+    # header bytes follow LZ4FrameWriter.cs:64-102: magic, FLG = version 01 | independent | flags, BD = 4 << 4, HC
+    f = F.write_frame(datas[3], 65536, True, True)
+    assert f[:6] == bytes([0x04, 0x22, 0x4D, 0x18, 0x40 | 0x20 | 0x10 | 0x04, 0x40])
+    assert f[6] == (port.xxh32(np.frombuffer(f[4:6], dtype=np.uint8), 0) >> 8) & 0xFF
+    # the incompressible block is stored raw (bit 31 of its length code), blocking.cs:22-33 / LZ4EncoderBase.cs:79-83
+    g = F.write_frame(datas[4], 65536, False, False)
+    import struct
+    assert struct.unpack_from("<I", g, 7)[0] == 0x80000000 | 65536
+    # corruption: block payload, block checksum, header checksum, content checksum
+    for at in (20, len(f) - 3, 6):
+        bad = bytearray(f); bad[at] ^= 0x55
+        with pytest.raises(F.InvalidDataException):
+            F.read_frame(bytes(bad))
+    # per-block checksums of a big batch: GPU XXH32 == restatement
+    blocks = [datas[5][i:i + 65536] for i in range(0, len(datas[5]), 65536)]
+    base = np.frombuffer(datas[5], dtype=np.uint8)
+    got = F.xxh32_batch(base, np.arange(5) * 65536, np.array([65536, 65535, 17, 3, 0], dtype=np.int32), 9)
+    want = [port.xxh32(np.frombuffer(b[:n], dtype=np.uint8), 9) for b, n in zip(blocks, [65536, 65535, 17, 3, 0])]
+    assert got.tolist() == want
