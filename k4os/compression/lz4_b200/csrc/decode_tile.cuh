@@ -50,18 +50,17 @@ constexpr int TILE_PAD = 32;             // slack behind the tile: output shift 
 constexpr int DT_THREADS = K4_DT_THREADS;
 constexpr int DT_WARPS = DT_THREADS / 32;
 constexpr int DT_K = DT_THREADS;         // sequences per step
-#ifndef K4_DT_SEG
-#define K4_DT_SEG 128
-#endif
 #ifndef K4_DT_WARM
 #define K4_DT_WARM 256
 #endif
-constexpr int DT_SEG = K4_DT_SEG;        // compressed bytes per parse lane
 constexpr int DT_WARM = K4_DT_WARM;      // speculative warm-up before the segment
-#ifndef K4_DT_HUGE
-#define K4_DT_HUGE 512
+#ifndef K4_DT_NEARSPIN
+#define K4_DT_NEARSPIN 1
 #endif
-constexpr int DT_HUGE = K4_DT_HUGE;      // runs of at least this many bytes are copied word-wise by the whole warp
+#ifndef K4_DT_LSHORT
+#define K4_DT_LSHORT 32
+#endif
+constexpr int DT_LSHORT = K4_DT_LSHORT;  // runs up to this length are copied by the owning lane, longer ones by the warp
 constexpr int STAGE_SMALL = 40 * 1024;   // two CTAs per SM
 constexpr int STAGE_BIG = 65536 + 32;    // one CTA per SM: every block the tile path can take
 constexpr int DT_NMAX = 16384;           // sequences per block the tile tail can describe
@@ -85,15 +84,14 @@ __device__ unsigned long long g_decode_prof[32];
 #define DT_PROF_COUNT(slot, v) do {} while (0)
 #endif
 
+// Parse-lane granularity: every one of the 512 threads parses, so the serial chain per lane is as
+// short as the stage allows (40 KiB / 512 = 80 bytes; 64 KiB / 512 = 128 bytes).
+template <int STAGE> struct TileCfg { static constexpr int SEG = STAGE <= 40 * 1024 ? 80 : 128; };
+
 template <int STAGE>
 struct TileSmem {
-    static constexpr int MAXSEG = (STAGE + DT_SEG - 1) / DT_SEG + 1;
     alignas(128) uint8_t tile[TILE_BYTES + TILE_PAD];
     alignas(16) uint8_t stage[STAGE];
-    uint32_t segOut[MAXSEG];             // output bytes of the sequences starting in the segment
-    uint16_t segEntry[MAXSEG];           // first chain position >= segment start
-    uint16_t segExit[MAXSEG];            // first chain position >= segment end
-    uint16_t segN[MAXSEG];               // sequences starting in the segment | bad << 15
     uint32_t nearIv[DT_K];               // destFirst | destLast << 16, sorted
     uint16_t nearOff[DT_K];              // match distance of the entry
     uint8_t nearFlag[DT_K];              // 1 = still pending
@@ -102,6 +100,9 @@ struct TileSmem {
     uint32_t nearCnt[2][DT_WARPS];       // per-warp near-match counts, double-buffered by step parity
     alignas(8) unsigned long long bar;
 };
+// While a block is parsed the output tile is empty; its head holds the per-lane sequence records,
+// the region from SEGX_BASE on the per-segment exits (the descriptors later grow down from the end).
+constexpr uint32_t SEGX_BASE = 60 * 1024;
 
 static_assert(sizeof(TileSmem<STAGE_SMALL>) <= 115712, "two CTAs per SM: (228 KiB - 2 x 1 KiB) / 2");
 static_assert(sizeof(TileSmem<STAGE_BIG>) <= 232448, "one CTA per SM: 227 KiB");
@@ -138,91 +139,96 @@ __device__ __forceinline__ void tma_store(void* gdst, const void* ssrc, int byte
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- shared memory by 32-bit shared-space address -----------------------------------------------
+// Every hot access goes through these: with generic pointers into the dynamic shared array nvcc
+// re-materialises the shared-window base (S2R SR_CgaCtaId, MOV, LEA, IADD) in front of EVERY
+// predicated byte access -- measured: 4-5 extra instructions per byte moved, 210 K warp instructions
+// per block instead of ~50 K (profiles/ncu_r02_*).  A shared address computed once costs nothing.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+// the compressed stream is read-only while it is parsed: no memory clobber (ordinary memory operations
+// may move across these loads); still volatile, so they stay behind the barrier that publishes the stage
+__device__ __forceinline__ uint32_t lds32_ro(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds8_ro(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+
 // ---- sequence header ------------------------------------------------------------------------
-// Header of the sequence whose token sits at stream position p (stage4 = the stage as aligned
-// words, stg[x] = stream byte x, sx = shift): two unaligned 4-byte windows -- token + first
-// length byte, offset + first match-length byte -- decode the common case without a branch; only
-// 255-chains take the byte loop.  ml includes MINMATCH and is 0 for the terminal (literal-only)
-// sequence.  flags: SQ_LAST terminal, SQ_BAD the stream cannot be a clean block, SQ_EDGE (EXACT
-// only) one of the reference's length-overrun tests would fire (LL.tools.cs:165-193,
-// LL64.dec.cs:231-232,329-331).  Every access stays below stream position n + 8.
+// Header of the sequence whose token sits at stream position p; sStg = shared address of stream
+// byte 0.  Two unaligned 4-byte windows -- token + first length byte, offset + first match-length
+// byte -- decode the common case without a branch; only 255-chains take the byte loop.  ml includes
+// MINMATCH and is 0 for the terminal (literal-only) sequence.  flags: SQ_LAST terminal, SQ_BAD the
+// stream cannot be a clean block, SQ_EDGE (EXACT only) one of the reference's length-overrun tests
+// would fire (LL.tools.cs:165-193, LL64.dec.cs:231-232,329-331).  Every access stays below stream
+// position n + 8.
 constexpr int SQ_EDGE = 4;
-__device__ __forceinline__ uint32_t stage_load4(const uint32_t* stage4, const int x) {
-    const uint32_t w0 = stage4[x >> 2], w1 = stage4[(x >> 2) + 1];
-    return __funnelshift_r(w0, w1, (x & 3) * 8);
+__device__ __forceinline__ uint32_t stage_load4(const uint32_t sStg, const int p) {
+    const uint32_t a = sStg + (uint32_t)p;
+    const uint32_t w0 = lds32_ro(a & ~3u), w1 = lds32_ro((a & ~3u) + 4u);
+    return __funnelshift_r(w0, w1, (a & 3u) * 8u);
 }
 template <bool EXACT>
-__device__ __forceinline__ void seq_header(const uint32_t* stage4, const uint8_t* stg, const int sx,
-                                           const int p, const int n, int& lit, int& litPos, int& ml,
-                                           int& off, int& next, uint32_t& flags) {
-    const uint32_t w = stage_load4(stage4, sx + p);
-    const uint32_t tok = w & 0xFFu;
-    int q = p + 1;
-    lit = (int)(tok >> 4);
-    flags = 0;
-    if (lit == 15) {
-        const uint32_t e1 = (w >> 8) & 0xFFu;
-        if (EXACT && q >= n - 15) flags |= SQ_EDGE;            // initial overrun
-        lit += (int)e1; q++;
-        if (e1 == 255u) {                                       // rare: >= 270 literals
-            if (EXACT && q >= n - 15) flags |= SQ_EDGE;
-            while (q < n) {
-                const uint32_t s = stg[q]; q++; lit += (int)s;
-                if (s != 255u) break;
-                if (EXACT && q >= n - 15) flags |= SQ_EDGE;    // the reference stops early here
-            }
-        }
+__device__ __forceinline__ void seq_header(const uint32_t sStg, const int p, const int n, int& lit,
+                                           int& litPos, int& ml, int& off, int& next, uint32_t& flags) {
+    // literal length: token nibble + up to three extension bytes straight from the first window
+    const uint32_t w = stage_load4(sStg, p);
+    const uint32_t tok = w & 0xFFu, e1 = (w >> 8) & 0xFFu, e2 = (w >> 16) & 0xFFu, e3 = w >> 24;
+    const bool l15 = (tok >> 4) == 15u;
+    const bool l2 = l15 && e1 == 255u, l3 = l2 && e2 == 255u;
+    lit = (int)(tok >> 4) + (l15 ? (int)e1 : 0) + (l2 ? (int)e2 : 0) + (l3 ? (int)e3 : 0);
+    int q = p + 1 + (l15 ? 1 : 0) + (l2 ? 1 : 0) + (l3 ? 1 : 0);
+    if (l3 && e3 == 255u) {                                     // rare: >= 780 literals, byte loop
+        while (q < n) { const uint32_t s = lds8_ro(sStg + q); q++; lit += (int)s; if (s != 255u) break; }
     }
+    flags = 0;
+    // LZ4_readVLE (LL.tools.cs:165-193): fatal if the first extension byte sits at >= iend-15; stops early
+    // (the walker does not) if a 255 byte ends at >= iend-15.  With k bytes consumed at p+1 .. p+k = q-1
+    // both reduce to q-1 >= n-15 (the last byte, which is not 255, may sit anywhere).
+    if (EXACT && l15 && q - 1 >= n - 15) flags |= SQ_EDGE;
     litPos = q;
     const int litEnd = q + lit;
-    if (litEnd + 2 > n) {                                       // no room for an offset: terminal sequence
-        next = n; ml = 0; off = 0;
-        flags |= SQ_LAST | (litEnd != n ? SQ_BAD : 0);
-        return;
+    const bool last = litEnd + 2 > n;                           // no room for an offset: terminal sequence
+    // match length: second window at the offset (at p again for the terminal sequence: always in range)
+    const uint32_t w2 = stage_load4(sStg, last ? p : litEnd);
+    const uint32_t m1 = (w2 >> 16) & 0xFFu, m2 = w2 >> 24;
+    const bool m15 = (tok & 15u) == 15u;
+    const bool mm2 = m15 && m1 == 255u;
+    int mlen = (int)(tok & 15u) + (m15 ? (int)m1 : 0) + (mm2 ? (int)m2 : 0);
+    int q2 = litEnd + 2 + (m15 ? 1 : 0) + (mm2 ? 1 : 0);
+    if (mm2 && m2 == 255u && !last) {                           // rare: match of >= 529 bytes, byte loop
+        while (q2 < n) { const uint32_t s = lds8_ro(sStg + q2); q2++; mlen += (int)s; if (s != 255u) break; }
     }
-    const uint32_t w2 = stage_load4(stage4, sx + litEnd);
-    off = (int)(w2 & 0xFFFFu);
-    ml = (int)(tok & 15u);
-    q = litEnd + 2;
-    if (ml == 15) {
-        const uint32_t m1 = (w2 >> 16) & 0xFFu;
-        ml += (int)m1; q++;
-        if (EXACT && q >= n - 4) flags |= SQ_EDGE;             // any overrun is fatal in the reference
-        if (m1 == 255u) {
-            while (q < n) {
-                const uint32_t s = stg[q]; q++; ml += (int)s;
-                if (EXACT && q >= n - 4) flags |= SQ_EDGE;
-                if (s != 255u) break;
-            }
-        }
-    }
-    ml += MINMATCH;
-    if (q >= n) flags |= SQ_BAD;                                // a block never ends with a match
-    next = q < n ? q : n;
+    if (EXACT && m15 && q2 >= n - 4) flags |= SQ_EDGE;           // any overrun is fatal in the reference (:326-334)
+    off = last ? 0 : (int)(w2 & 0xFFFFu);
+    ml = last ? 0 : mlen + MINMATCH;
+    next = last ? n : (q2 < n ? q2 : n);
+    flags |= last ? (uint32_t)(SQ_LAST | (litEnd != n ? SQ_BAD : 0)) : (q2 >= n ? (uint32_t)SQ_BAD : 0u);   // a block never ends with a match
 }
 
-// ---- copies inside shared memory ------------------------------------------------------------
+// ---- copies inside shared memory (all addresses are 32-bit shared addresses) -------------------
 // whole warp, uniform arguments, source and destination do not overlap: destination-aligned
 // 4-byte words built from two aligned source words
-__device__ __forceinline__ void warp_copy(uint8_t* d, const uint8_t* s, int len, const int lane) {
-    const int h0 = (int)((4u - ((uint32_t)(uintptr_t)d & 3u)) & 3u);
+__device__ __forceinline__ void warp_copy(uint32_t d, uint32_t s, int len, const int lane) {
+    const int h0 = (int)((4u - (d & 3u)) & 3u);
     const int h = h0 < len ? h0 : len;
-    if (lane < h) d[lane] = s[lane];
+    if (lane < h) sts8(d + lane, lds8(s + lane));
     d += h; s += h; len -= h;
     const int nw = len >> 2;
-    const uint32_t sh = ((uint32_t)(uintptr_t)s & 3u) * 8u;
-    const uint32_t* s4 = reinterpret_cast<const uint32_t*>(s - (sh >> 3));
-    uint32_t* d4 = reinterpret_cast<uint32_t*>(d);
+    const uint32_t sh = (s & 3u) * 8u;
+    const uint32_t sa = s & ~3u;
     for (int w = lane; w < nw; w += 32) {
-        const uint32_t lo = s4[w];
-        const uint32_t hi = sh ? s4[w + 1] : 0u;
-        d4[w] = __funnelshift_r(lo, hi, sh);
+        const uint32_t lo = lds32(sa + 4u * w);
+        const uint32_t hi = sh ? lds32(sa + 4u * w + 4u) : 0u;
+        sts32(d + 4u * w, __funnelshift_r(lo, hi, sh));
     }
     const int t = len & 3;
-    if (lane < t) d[4 * nw + lane] = s[4 * nw + lane];
+    if (lane < t) sts8(d + 4u * nw + lane, lds8(s + 4u * nw + lane));
 }
 // whole warp, LZ77 match of `len` bytes at d with distance off (uniform arguments)
-__device__ __forceinline__ void warp_copy_match_smem(uint8_t* d, const int off, const int len, const int lane) {
+__device__ __forceinline__ void warp_copy_match_smem(uint32_t d, const int off, const int len, const int lane) {
     if (off >= len) { warp_copy(d, d - off, len, lane); return; }
     if (off >= 160) {
         // overlapping but far enough apart: 128-byte slices, each one reads only bytes that earlier
@@ -234,52 +240,23 @@ __device__ __forceinline__ void warp_copy_match_smem(uint8_t* d, const int off, 
         }
         return;
     }
-    const uint8_t* s = d - off;                 // periodic: every byte comes from the final window [d-off, d)
-    for (int i = lane; i < len; i += 32) d[i] = s[i % off];
+    const uint32_t s = d - off;                 // periodic: every byte comes from the final window [d-off, d)
+    for (int i = lane; i < len; i += 32) sts8(d + i, lds8(s + (i % off)));
 }
 
-// Balanced copy of many short runs by one warp.  Lane i owns an item made of c_i pieces of up to
-// DT_PIECE bytes; the pieces of all 32 items are numbered consecutively and handed out 32 at a
-// time, one per lane, so the work per lane is even no matter how the run lengths are distributed.
-// Owner lookup without shared memory: the non-empty lanes set a bit at their first piece number
-// (one warp OR-reduction per pass), a lane finds the rank of its piece's owner with a popcount and
-// the owner's lane through a rank -> lane table held in registers.  body(ownerLane, j, live) is
-// called by ALL lanes (it may shuffle); j = index of the piece inside the owner's item.
-#ifndef K4_DT_PIECE
-#define K4_DT_PIECE 8
-#endif
-constexpr int DT_PIECE = K4_DT_PIECE;
-template <class Body>
-__device__ __forceinline__ void warp_expand(const int c, const int lane, Body&& body) {
-    int incl = c;
-#pragma unroll
-    for (int dlt = 1; dlt < 32; dlt <<= 1) {
-        const int v = __shfl_up_sync(FULL, incl, dlt);
-        if (lane >= dlt) incl += v;
+// one lane, source and destination do not overlap: four bytes in flight per trip
+__device__ __forceinline__ void lane_copy(const uint32_t d, const uint32_t s, const int len) {
+    int j = 0;
+    for (; j + 4 <= len; j += 4) {
+        const uint32_t v0 = lds8(s + j), v1 = lds8(s + j + 1), v2 = lds8(s + j + 2), v3 = lds8(s + j + 3);
+        sts8(d + j, v0); sts8(d + j + 1, v1); sts8(d + j + 2, v2); sts8(d + j + 3, v3);
     }
-    const int total = __shfl_sync(FULL, incl, 31);
-    if (total == 0) return;
-    const int s = incl - c;                                      // first piece number of my item
-    const unsigned nz = __ballot_sync(FULL, c > 0);
-    const int rankToLane = (int)__fns(nz, 0, lane + 1);          // lane of the (lane+1)-th non-empty item
-    for (int base = 0; base < total; base += 32) {
-        const bool startsHere = c > 0 && s >= base && s < base + 32;
-        const unsigned M = __reduce_or_sync(FULL, startsHere ? 1u << (s - base) : 0u);
-        const int baseRank = __popc(__ballot_sync(FULL, c > 0 && s < base)) - 1;
-        const int g = base + lane;
-        const int ownerRank = baseRank + __popc(M & (0xFFFFFFFFu >> (31 - lane)));
-        const int ownerLane = __shfl_sync(FULL, rankToLane, ownerRank & 31);
-        const int sOwner = __shfl_sync(FULL, s, ownerLane & 31);
-        body(ownerLane & 31, g - sOwner, g < total);
-    }
+    for (; j < len; j++) sts8(d + j, lds8(s + j));
 }
-// one piece: up to DT_PIECE bytes, all loads before all stores
-__device__ __forceinline__ void piece_copy(uint8_t* dst, const uint8_t* src, const int len) {
-    uint8_t v[DT_PIECE];
-#pragma unroll
-    for (int j = 0; j < DT_PIECE; j++) if (j < len) v[j] = src[j];
-#pragma unroll
-    for (int j = 0; j < DT_PIECE; j++) if (j < len) dst[j] = v[j];
+// one lane, LZ77 semantics (the source may run into the destination): strictly byte by byte then
+__device__ __forceinline__ void lane_copy_match(const uint32_t d, const int off, const int len) {
+    if (off >= len) { lane_copy(d, d - (uint32_t)off, len); return; }
+    for (int j = 0; j < len; j++) sts8(d + j, lds8(d + j - (uint32_t)off));
 }
 
 // ---- the tile decoder ---------------------------------------------------------------------------
@@ -292,7 +269,7 @@ __device__ int tile_decode_block(TileSmem<STAGE>& S, const uint8_t* __restrict__
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int shift = (int)(reinterpret_cast<uintptr_t>(src) & 15);
     uint8_t* const stg = S.stage + shift;                       // stg[p] == src[p]
-    const uint32_t* const stage4 = reinterpret_cast<const uint32_t*>(S.stage);
+    const uint32_t sStg = smem_u32(S.stage) + (uint32_t)shift;  // shared address of stream byte 0
     DT_PROF_DECL
 
     // ---- compressed block -> shared memory: aligned middle by TMA, ragged ends by plain loads ----
@@ -313,48 +290,66 @@ __device__ int tile_decode_block(TileSmem<STAGE>& S, const uint8_t* __restrict__
     DT_PROF(0);
 
     // ---- 1. segmented speculative parse ------------------------------------------------------------
-    const int NS = (n + DT_SEG - 1) / DT_SEG;
-    const int segStart = tid * DT_SEG;
-    const int segEnd = segStart + DT_SEG < n ? segStart + DT_SEG : n;
+    constexpr int SEG = TileCfg<STAGE>::SEG;
+    const int NS = (n + SEG - 1) / SEG;                          // <= DT_THREADS by the caller's size test
+    const int segStart = tid * SEG;
+    const int segEnd = segStart + SEG < n ? segStart + SEG : n;
+    // per-lane record area in the (still unused) head of the tile: one u16 per sequence of the segment
+    constexpr uint32_t REC_STRIDE = 2u * (SEG / 3 + 3);
+    static_assert(REC_STRIDE * DT_THREADS <= SEGX_BASE, "records must stay below the exit array");
+    const uint32_t sRec = smem_u32(S.tile) + REC_STRIDE * (uint32_t)tid;
+    const uint32_t sExit = smem_u32(S.tile) + SEGX_BASE;          // u16 per segment, read across warps only
+    uint32_t myEntry = 0, myExit = 0, myCnt = 0, myOut = 0, myBad = 0;
     // walks from p to the end of the lane's segment; counts what starts inside the segment
     auto walk = [&](int p) {
         uint32_t entry = 0xFFFFFFFFu, cnt = 0, ob = 0, bad = 0;
         while (p < segEnd) {
             int lit, litPos, ml, off, nx; uint32_t fl;
-            seq_header<false>(stage4, stg, shift, p, n, lit, litPos, ml, off, nx, fl);
+            seq_header<false>(sStg, p, n, lit, litPos, ml, off, nx, fl);
             if (p >= segStart) {
                 entry = entry < (uint32_t)p ? entry : (uint32_t)p;
-                cnt++; ob += (uint32_t)(lit + ml); bad |= fl & SQ_BAD;
+                // remember the sequence's compressed and decoded length (255 = "too long, decode again"):
+                // pass 2 then is a short prefix loop over these records instead of a second parse
+                const uint32_t cl = (uint32_t)(nx - p), ol = (uint32_t)(lit + ml);
+                sts16(sRec + 2u * cnt, (cl < 255u ? cl : 255u) | ((ol < 255u ? ol : 255u) << 8));
+                cnt++; ob += ol; bad |= fl & SQ_BAD;
             }
             p = nx;
         }
-        S.segEntry[tid] = (uint16_t)(entry == 0xFFFFFFFFu ? (uint32_t)p : entry);
-        S.segExit[tid] = (uint16_t)p;
-        S.segN[tid] = (uint16_t)(cnt | (bad ? 0x8000u : 0u));
-        S.segOut[tid] = ob;
+        myEntry = entry == 0xFFFFFFFFu ? (uint32_t)p : entry;
+        myExit = (uint32_t)p; myCnt = cnt; myOut = ob; myBad = bad;
     };
-    if (tid < NS) walk(segStart > DT_WARM ? segStart - DT_WARM : 0);
+    const bool parses = tid < NS;
+    if (parses) { walk(segStart > DT_WARM ? segStart - DT_WARM : 0); sts16(sExit + 2u * tid, myExit); }
+    // Lane t is right iff entry[t] == exit[t-1].  Inside a warp the exits travel by shuffle and a chain of
+    // wrong lanes (a literal run that covers several whole segments makes every one of them wrong) is
+    // repaired without leaving the warp; across warps through the exit array, one CTA round per hop.
     for (int round = 0;; round++) {
         __syncthreads();
         if (round == 0) DT_PROF(1);
-        uint32_t e = 0;
-        bool wrong = false;
-        if (tid >= 1 && tid < NS) { e = S.segExit[tid - 1]; wrong = S.segEntry[tid] != e; }
-        if (!__syncthreads_or(wrong)) break;
-        if (round > NS + 1) return -1;                          // cannot happen: lane t is final after round t
-        if (wrong) {
-            walk((int)e);
+        bool walked = false;
+        for (int it = 0; it < 34; it++) {
+            uint32_t e = __shfl_up_sync(FULL, myExit, 1);
+            if (lane == 0) e = tid > 0 && parses ? lds16(sExit + 2u * (tid - 1)) : 0u;
+            const bool wrong = parses && tid >= 1 && myEntry != e;
+            if (!__any_sync(FULL, wrong)) break;
+            if (wrong) {
+                walk((int)e);
 #ifdef K4_DT_PROFILE
-            atomicAdd(&g_decode_stats[3], 1ull);
+                atomicAdd(&g_decode_stats[3], 1ull);
 #endif
+            }
+            walked = true;
         }
+        if (walked && parses) sts16(sExit + 2u * tid, myExit);
         DT_PROF_COUNT(16, 1);
+        if (!__syncthreads_or(walked)) break;                   // a full round without a single re-walk: all links agree
+        if (round > NS + 1) return -1;                          // cannot happen: lane t is final after round t
     }
     DT_PROF(2);
 
     // ---- 2. block-wide exclusive scan of (sequence count, output bytes) per segment ----------------
-    uint32_t cIn = 0, oIn = 0, badSeg = 0;
-    if (tid < NS) { const uint32_t v = S.segN[tid]; cIn = v & 0x7FFFu; badSeg = v >> 15; oIn = S.segOut[tid]; }
+    const uint32_t cIn = parses ? myCnt : 0u, oIn = parses ? myOut : 0u, badSeg = parses ? myBad : 0u;
     uint32_t cInc = cIn, oInc = oIn;
 #pragma unroll
     for (int dlt = 1; dlt < 32; dlt <<= 1) {
@@ -377,17 +372,33 @@ __device__ int tile_decode_block(TileSmem<STAGE>& S, const uint8_t* __restrict__
     DT_PROF(3);
 
     // descriptors: desc[i] = tokenPos | outPos << 16, in the tail of the tile
-    uint32_t* const desc = reinterpret_cast<uint32_t*>(S.tile + TILE_BYTES + TILE_PAD) - N;
+    const uint32_t sDesc = smem_u32(S.tile) + (uint32_t)(TILE_BYTES + TILE_PAD) - 4u * (uint32_t)N;   // &desc[0]
+    const bool recordsIntact = 4u * (uint32_t)N + REC_STRIDE * (uint32_t)NS <= (uint32_t)(TILE_BYTES + TILE_PAD);
     if (tid < NS) {
-        int p = (int)S.segEntry[tid];
+        int p = (int)myEntry;
         uint32_t idx = cBase + cInc - cIn;
         int op = (int)(oBase + oInc - oIn);
-        while (p < segEnd) {
-            int lit, litPos, ml, off, nx; uint32_t fl;
-            seq_header<false>(stage4, stg, shift, p, n, lit, litPos, ml, off, nx, fl);
-            desc[idx++] = (uint32_t)p | ((uint32_t)(op < 65535 ? op : 65535) << 16);
-            op += lit + ml;
-            p = nx;
+        if (recordsIntact) {                                     // the descriptors do not reach down to the records
+            for (uint32_t k = 0; k < cIn; k++) {
+                const uint32_t rec = lds16(sRec + 2u * k);
+                int cl = (int)(rec & 255u), ol = (int)(rec >> 8);
+                if (cl == 255 || ol == 255) {                    // rare: a long sequence, decode it again
+                    int lit, litPos, ml, off, nx; uint32_t fl;
+                    seq_header<false>(sStg, p, n, lit, litPos, ml, off, nx, fl);
+                    cl = nx - p; ol = lit + ml;
+                }
+                sts32(sDesc + 4u * idx, (uint32_t)p | ((uint32_t)(op < 65535 ? op : 65535) << 16));
+                idx++; p += cl; op += ol;
+            }
+        } else {
+            while (p < segEnd) {
+                int lit, litPos, ml, off, nx; uint32_t fl;
+                seq_header<false>(sStg, p, n, lit, litPos, ml, off, nx, fl);
+                sts32(sDesc + 4u * idx, (uint32_t)p | ((uint32_t)(op < 65535 ? op : 65535) << 16));
+                idx++;
+                op += lit + ml;
+                p = nx;
+            }
         }
     }
     __syncthreads();
@@ -396,14 +407,16 @@ __device__ int tile_decode_block(TileSmem<STAGE>& S, const uint8_t* __restrict__
     // ---- 3. steps of DT_K sequences ----------------------------------------------------------------
     const int tshift = (int)(reinterpret_cast<uintptr_t>(gdst) & 15);
     uint8_t* const T = S.tile + tshift;                          // T[op] is output byte op
+    const uint32_t sT = smem_u32(S.tile) + (uint32_t)tshift;     // shared address of output byte 0
+    const uint32_t sNearIv = smem_u32(S.nearIv), sNearOff = smem_u32(S.nearOff), sNearFlag = smem_u32(S.nearFlag);
     const int nsteps = (N + DT_K - 1) / DT_K;
-    uint32_t dCur = tid < N ? desc[tid] : 0u;
+    uint32_t dCur = tid < N ? lds32(sDesc + 4u * tid) : 0u;
     int Sr = 0;                                                  // output position where the step begins
     for (int r = 0; r < nsteps; r++) {
         const int i = r * DT_K + tid;
         const bool valid = i < N;
-        const uint32_t dNext = i + DT_K < N ? desc[i + DT_K] : 0u;   // intact until the next step writes
-        const int SrNext = (r + 1) * DT_K < N ? (int)(desc[(r + 1) * DT_K] >> 16) : O;
+        const uint32_t dNext = i + DT_K < N ? lds32(sDesc + 4u * (i + DT_K)) : 0u;   // intact until the next step writes
+        const int SrNext = (r + 1) * DT_K < N ? (int)(lds32(sDesc + 4u * ((r + 1) * DT_K)) >> 16) : O;
 
         // sequence header, with the reference's accept tests (conservative: see file header)
         int lit = 0, ml = 0, off = 0, litPos = 0, op = 0;
@@ -412,7 +425,7 @@ __device__ int tile_decode_block(TileSmem<STAGE>& S, const uint8_t* __restrict__
             const int tp = (int)(dCur & 0xFFFFu);
             op = (int)(dCur >> 16);
             int nx; uint32_t fl;
-            seq_header<true>(stage4, stg, shift, tp, n, lit, litPos, ml, off, nx, fl);
+            seq_header<true>(sStg, tp, n, lit, litPos, ml, off, nx, fl);
             bad = (fl & (SQ_EDGE | SQ_BAD)) != 0;
             if (i == N - 1) {                                    // terminal: LL64.dec.cs:247-294
                 if (!(fl & SQ_LAST) || op + lit > cap) bad = true;
@@ -430,41 +443,18 @@ __device__ int tile_decode_block(TileSmem<STAGE>& S, const uint8_t* __restrict__
         const int srcEnd = a + ml < d ? a + ml : d;              // bytes read from outside the match itself: [a, srcEnd)
         const bool nearM = ml > 0 && srcEnd > Sr;
         const bool farM = ml > 0 && !nearM;
-        const bool farPieces = farM && off >= ml && ml < DT_HUGE;   // plain copy of moderate size
-        const bool litPieces = lit < DT_HUGE;
 
-        // literals and far matches as evenly distributed pieces
-        {
-            const int cl = litPieces ? (lit + DT_PIECE - 1) / DT_PIECE : 0;
-            const int cm = farPieces ? (ml + DT_PIECE - 1) / DT_PIECE : 0;
-            const uint32_t P1 = (uint32_t)litPos | ((uint32_t)op << 16);
-            const uint32_t P2 = (uint32_t)(litPieces ? lit : 0) | ((uint32_t)(farPieces ? ml : 0) << 16);
-            const uint32_t P3 = (uint32_t)off | ((uint32_t)cl << 16);
-            warp_expand(cl + cm, lane, [&](const int owner, const int j, const bool live) {
-                const uint32_t p1 = __shfl_sync(FULL, P1, owner), p2 = __shfl_sync(FULL, P2, owner),
-                               p3 = __shfl_sync(FULL, P3, owner);
-                const int oLitPos = (int)(p1 & 0xFFFFu), oOp = (int)(p1 >> 16);
-                const int oLit = (int)(p2 & 0xFFFFu), oMl = (int)(p2 >> 16);
-                const int oOff = (int)(p3 & 0xFFFFu), oCl = (int)(p3 >> 16);
-                const bool isLit = j < oCl;
-                const int k = (isLit ? j : j - oCl) * DT_PIECE;
-                const int run = isLit ? oLit : oMl;
-                int len = run - k; len = len > DT_PIECE ? DT_PIECE : len;
-                if (!live) len = 0;
-                const int dpos = (isLit ? oOp : oOp + oLit) + k;
-                const uint8_t* sp = isLit ? stg + oLitPos + k : T + dpos - oOff;
-                piece_copy(T + dpos, sp, len);
-            });
+        // literals, then far matches: short runs by the owning lane, long ones by the whole warp
+        if (lit > 0 && lit <= DT_LSHORT) lane_copy(sT + (uint32_t)op, sStg + (uint32_t)litPos, lit);
+        for (unsigned m = __ballot_sync(FULL, lit > DT_LSHORT); m; m &= m - 1) {
+            const int l = __ffs(m) - 1;
+            warp_copy(sT + (uint32_t)__shfl_sync(FULL, op, l), sStg + (uint32_t)__shfl_sync(FULL, litPos, l), __shfl_sync(FULL, lit, l), lane);
         }
         DT_PROF(6);
-        // the rest by the whole warp: huge literal runs, overlapping or huge far matches
-        for (unsigned m = __ballot_sync(FULL, !litPieces); m; m &= m - 1) {
+        if (farM && ml <= DT_LSHORT) lane_copy_match(sT + (uint32_t)d, off, ml);
+        for (unsigned m = __ballot_sync(FULL, farM && ml > DT_LSHORT); m; m &= m - 1) {
             const int l = __ffs(m) - 1;
-            warp_copy(T + __shfl_sync(FULL, op, l), stg + __shfl_sync(FULL, litPos, l), __shfl_sync(FULL, lit, l), lane);
-        }
-        for (unsigned m = __ballot_sync(FULL, farM && !farPieces); m; m &= m - 1) {
-            const int l = __ffs(m) - 1;
-            warp_copy_match_smem(T + __shfl_sync(FULL, d, l), __shfl_sync(FULL, off, l), __shfl_sync(FULL, ml, l), lane);
+            warp_copy_match_smem(sT + (uint32_t)__shfl_sync(FULL, d, l), __shfl_sync(FULL, off, l), __shfl_sync(FULL, ml, l), lane);
         }
         const unsigned nearBallot = __ballot_sync(FULL, nearM);
         if (lane == 0) S.nearCnt[r & 1][warp] = (uint32_t)__popc(nearBallot);
@@ -485,29 +475,27 @@ __device__ int tile_decode_block(TileSmem<STAGE>& S, const uint8_t* __restrict__
             const int nearBase = warp ? (int)__shfl_sync(FULL, nc, warp - 1) : 0;   // all lanes: no shuffle under divergence
             if (nearM) {
                 const int me = nearBase + __popc(nearBallot & ((1u << lane) - 1u));
-                S.nearIv[me] = (uint32_t)d | ((uint32_t)(d + ml - 1) << 16);
-                S.nearOff[me] = (uint16_t)off;
-                S.nearFlag[me] = 1;
+                sts32(sNearIv + 4u * me, (uint32_t)d | ((uint32_t)(d + ml - 1) << 16));
+                sts16(sNearOff + 2u * me, (uint32_t)off);
+                sts8(sNearFlag + me, 1u);
             }
             __syncthreads();                                     // barrier #2: list complete
             // entry `tid` of the list is mine from here on
             const bool mine = tid < nearTotal;
             int nd = 0, nml = 0, noff = 1, lo = 0, hi = 0;
             if (mine) {
-                const uint32_t iv = S.nearIv[tid];
-                nd = (int)(iv & 0xFFFFu); nml = (int)(iv >> 16) - nd + 1; noff = (int)S.nearOff[tid];
+                const uint32_t iv = lds32(sNearIv + 4u * tid);
+                nd = (int)(iv & 0xFFFFu); nml = (int)(iv >> 16) - nd + 1; noff = (int)lds16(sNearOff + 2u * tid);
                 const int na = nd - noff;
                 const int nSrcEnd = na + nml < nd ? na + nml : nd;
                 // pending intervals before mine that intersect my source [na, nSrcEnd)
                 int x = 0, y = tid;
-                while (x < y) { const int mid = (x + y) >> 1; if ((int)(S.nearIv[mid] >> 16) >= na) y = mid; else x = mid + 1; }
+                while (x < y) { const int mid = (x + y) >> 1; if ((int)(lds32(sNearIv + 4u * mid) >> 16) >= na) y = mid; else x = mid + 1; }
                 lo = x; hi = lo;
-                while (hi < tid && (int)(S.nearIv[hi] & 0xFFFFu) < nSrcEnd) hi++;
+                while (hi < tid && (int)(lds32(sNearIv + 4u * hi) & 0xFFFFu) < nSrcEnd) hi++;
             }
             bool pend = mine;
-            const bool plain = noff >= nml && nml < DT_HUGE;
             DT_PROF(9);
-            const volatile uint8_t* flags = S.nearFlag;
             const bool warpHasWork = warp * 32 < nearTotal;
             for (int round = 0;; round++) {
                 if (warpHasWork) {
@@ -515,42 +503,44 @@ __device__ int tile_decode_block(TileSmem<STAGE>& S, const uint8_t* __restrict__
                     do {
                         bool go = pend;
                         if (go) {
-                            while (lo < hi && !flags[lo]) lo++;
+                            while (lo < hi && !lds8(sNearFlag + lo)) lo++;
                             go = lo >= hi;
                         }
                         __threadfence_block();                   // bytes behind the cleared flags
-                        {
-                            const uint32_t Q1 = (uint32_t)nd | ((uint32_t)nml << 16);
-                            warp_expand(go && plain ? (nml + DT_PIECE - 1) / DT_PIECE : 0, lane,
-                                        [&](const int owner, const int j, const bool live) {
-                                const uint32_t q1 = __shfl_sync(FULL, Q1, owner);
-                                const int oOff = __shfl_sync(FULL, noff, owner);
-                                const int k = j * DT_PIECE;
-                                int len = (int)(q1 >> 16) - k; len = len > DT_PIECE ? DT_PIECE : len;
-                                if (!live) len = 0;
-                                const int dpos = (int)(q1 & 0xFFFFu) + k;
-                                piece_copy(T + dpos, T + dpos - oOff, len);
-                            });
-                        }
-                        for (unsigned m = __ballot_sync(FULL, go && !plain); m; m &= m - 1) {
+                        if (go && nml <= DT_LSHORT) lane_copy_match(sT + (uint32_t)nd, noff, nml);
+                        for (unsigned m = __ballot_sync(FULL, go && nml > DT_LSHORT); m; m &= m - 1) {
                             const int l = __ffs(m) - 1;
-                            warp_copy_match_smem(T + __shfl_sync(FULL, nd, l), __shfl_sync(FULL, noff, l), __shfl_sync(FULL, nml, l), lane);
+                            warp_copy_match_smem(sT + (uint32_t)__shfl_sync(FULL, nd, l), __shfl_sync(FULL, noff, l), __shfl_sync(FULL, nml, l), lane);
                         }
                         __threadfence_block();
                         __syncwarp();
-                        if (go) { S.nearFlag[tid] = 0; pend = false; }
+                        if (go) { sts8(sNearFlag + tid, 0u); pend = false; }
                         __syncwarp();
                         progress = __any_sync(FULL, go);
                         DT_PROF_COUNT(19, 1);
                     } while (progress && __any_sync(FULL, pend));
                 }
                 DT_PROF(10);
+#if K4_DT_NEARSPIN
+                // no CTA barrier between rounds: a pending entry only ever waits for entries with a LOWER
+                // index (same warp, lower lane, or an earlier warp), entry 0 waits for nothing, so polling
+                // the flags terminates; one barrier after the loop publishes the step
+                if (!warpHasWork || !__any_sync(FULL, pend)) break;
+                __nanosleep(40);
+                DT_PROF_COUNT(18, 1);
+                if (round > (1 << 20)) break;                     // (bounded for safety; never reached)
+#else
                 const bool more = __syncthreads_or(pend);
                 DT_PROF(11);
                 DT_PROF_COUNT(18, 1);
                 if (!more) break;
                 if (round > DT_K + 2) return -1;                 // cannot happen: each round retires the first pending match
+#endif
             }
+#if K4_DT_NEARSPIN
+            __syncthreads();
+            DT_PROF(11);
+#endif
         }
         dCur = dNext;
         Sr = SrNext;
