@@ -55,6 +55,7 @@ MP_ENCODE = 0.55                # ... ratio ~0.57 "Silesia-like" (configs[2])
 SEED = 1234
 CHUNK_BLOCKS = 1024             # generator streams are 64 MiB long
 METRIC = "GB/s uncompressed (encode+decode) on batched 64KiB blocks @1/2/4/8 GPU vs CPU ref"
+ALL_CPUS = os.sched_getaffinity(0)     # before any NUMA binding
 
 
 # ---- pure helpers (unit-tested on CPU, tests/test_host_logic.py) --------------------------------
@@ -322,7 +323,7 @@ def all_devices_leg(torch, N, L, h_comp, comp_bytes, h_comp_len, h_raw_enc, nb, 
     import ctypes
     ndev = torch.cuda.device_count()
     try:
-        os.sched_setaffinity(0, range(os.cpu_count() or 1))     # rank 0 was bound to GPU 0's node
+        os.sched_setaffinity(0, ALL_CPUS)                        # rank 0 was bound to GPU 0's node
     except OSError:
         pass
     comp_sl, out_sl, raw_sl, slot_sl = [None] * ndev, [None] * ndev, [None] * ndev, [None] * ndev
@@ -341,7 +342,7 @@ def all_devices_leg(torch, N, L, h_comp, comp_bytes, h_comp_len, h_raw_enc, nb, 
     for t in ths:
         t.join()
     try:
-        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+        os.sched_setaffinity(0, ALL_CPUS)
     except OSError:
         pass
     n = ndev * nb
@@ -397,8 +398,10 @@ def run_ours(args) -> None:
     numa = bind_to_gpu_numa_node(local) if not args.no_numa else "numa: binding disabled"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")   # host-side waits that keep the GPUs idle (aux leg below)
     L = N.lib()
     nb = args.blocks
     total_blocks = nb * world
@@ -548,8 +551,10 @@ def run_ours(args) -> None:
     # ---- aux: the product's own multi-GPU path -- ONE k4lz4_decode_batch / k4lz4_encode_batch call with
     # K4LZ4_ALL_DEVICES over world x nb blocks (rank 0 only; the other ranks idle at the barrier below).
     # Host buffers are allocated per GPU slice by a thread pinned to that GPU's NUMA node.
+    # (the other ranks wait on a gloo barrier: an NCCL barrier would keep a polling kernel on their GPUs)
     if world > 1:
-        dist.barrier()
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)
     if rank == 0 and args.all_devices and torch.cuda.device_count() > 1:
         try:
             aux["all_devices_one_call"] = all_devices_leg(torch, N, L, h_comp, comp_bytes, h_comp_len, h_raw_enc, nb,
@@ -557,7 +562,7 @@ def run_ours(args) -> None:
         except Exception as e:   # noqa: BLE001
             aux["all_devices_one_call"] = {"error": f"{type(e).__name__}: {e}"}
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=cpu_group)
 
     # ---- aux: pickler (configs[3]) device-resident throughput ----
     try:
@@ -600,6 +605,10 @@ def run_ours(args) -> None:
     # ---- cpu baseline on rank 0 at N = 1: bounded sample of the same step ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:                                        # the rank was bound to its GPU's NUMA node: the CPU leg gets every core
+            os.sched_setaffinity(0, ALL_CPUS)
+        except OSError:
+            pass
         threads = len(os.sched_getaffinity(0)) or 1
         sb = min(16384, nb)
         w = CpuWorkload(sb, lo, threads)

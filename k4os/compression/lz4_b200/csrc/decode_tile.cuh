@@ -208,6 +208,35 @@ __device__ __forceinline__ void seq_header(const uint32_t sStg, const int p, con
     flags |= last ? (uint32_t)(SQ_LAST | (litEnd != n ? SQ_BAD : 0)) : (q2 >= n ? (uint32_t)SQ_BAD : 0u);   // a block never ends with a match
 }
 
+// The walker's view of the same header: only where the next token sits and how many bytes the
+// sequence produces (the parse runs tens of these hops back to back per lane; every instruction on
+// that path costs latency).  Must agree with seq_header on `next` and lit + ml for every input.
+__device__ __forceinline__ void seq_next(const uint32_t sStg, const int p, const int n, int& next, int& outb, uint32_t& bad) {
+    const uint32_t w = stage_load4(sStg, p);
+    const uint32_t tok = w & 0xFFu, e1 = (w >> 8) & 0xFFu, e2 = (w >> 16) & 0xFFu, e3 = w >> 24;
+    const bool l15 = (tok >> 4) == 15u;
+    const bool l2 = l15 && e1 == 255u, l3 = l2 && e2 == 255u;
+    int lit = (int)(tok >> 4) + (l15 ? (int)e1 : 0) + (l2 ? (int)e2 : 0) + (l3 ? (int)e3 : 0);
+    int q = p + 1 + (l15 ? 1 : 0) + (l2 ? 1 : 0) + (l3 ? 1 : 0);
+    if (l3 && e3 == 255u) {
+        while (q < n) { const uint32_t s = lds8_ro(sStg + q); q++; lit += (int)s; if (s != 255u) break; }
+    }
+    const int litEnd = q + lit;
+    const bool last = litEnd + 2 > n;
+    const uint32_t w2 = stage_load4(sStg, last ? p : litEnd);
+    const uint32_t m1 = (w2 >> 16) & 0xFFu, m2 = w2 >> 24;
+    const bool m15 = (tok & 15u) == 15u;
+    const bool mm2 = m15 && m1 == 255u;
+    int mlen = (int)(tok & 15u) + (m15 ? (int)m1 : 0) + (mm2 ? (int)m2 : 0);
+    int q2 = litEnd + 2 + (m15 ? 1 : 0) + (mm2 ? 1 : 0);
+    if (mm2 && m2 == 255u && !last) {
+        while (q2 < n) { const uint32_t s = lds8_ro(sStg + q2); q2++; mlen += (int)s; if (s != 255u) break; }
+    }
+    next = last ? n : (q2 < n ? q2 : n);
+    outb = lit + (last ? 0 : mlen + MINMATCH);
+    bad = last ? (litEnd != n ? 1u : 0u) : (q2 >= n ? 1u : 0u);
+}
+
 // ---- copies inside shared memory (all addresses are 32-bit shared addresses) -------------------
 // whole warp, uniform arguments, source and destination do not overlap: destination-aligned
 // 4-byte words built from two aligned source words
@@ -303,20 +332,23 @@ __device__ int tile_decode_block(TileSmem<STAGE>& S, const uint8_t* __restrict__
     // walks from p to the end of the lane's segment; counts what starts inside the segment
     auto walk = [&](int p) {
         uint32_t entry = 0xFFFFFFFFu, cnt = 0, ob = 0, bad = 0;
-        while (p < segEnd) {
-            int lit, litPos, ml, off, nx; uint32_t fl;
-            seq_header<false>(sStg, p, n, lit, litPos, ml, off, nx, fl);
-            if (p >= segStart) {
-                entry = entry < (uint32_t)p ? entry : (uint32_t)p;
-                // remember the sequence's compressed and decoded length (255 = "too long, decode again"):
-                // pass 2 then is a short prefix loop over these records instead of a second parse
-                const uint32_t cl = (uint32_t)(nx - p), ol = (uint32_t)(lit + ml);
-                sts16(sRec + 2u * cnt, (cl < 255u ? cl : 255u) | ((ol < 255u ? ol : 255u) << 8));
-                cnt++; ob += ol; bad |= fl & SQ_BAD;
-            }
+        while (p < segStart) {                                   // warm-up: only the position matters
+            int nx, o; uint32_t b;
+            seq_next(sStg, p, n, nx, o, b);
             p = nx;
         }
-        myEntry = entry == 0xFFFFFFFFu ? (uint32_t)p : entry;
+        entry = (uint32_t)p;                                     // first position >= segStart
+        while (p < segEnd) {
+            int nx, o; uint32_t b;
+            seq_next(sStg, p, n, nx, o, b);
+            // remember the sequence's compressed and decoded length (255 = "too long, decode again"):
+            // pass 2 then is a short prefix loop over these records instead of a second parse
+            const uint32_t cl = (uint32_t)(nx - p), ol = (uint32_t)o;
+            sts16(sRec + 2u * cnt, (cl < 255u ? cl : 255u) | ((ol < 255u ? ol : 255u) << 8));
+            cnt++; ob += ol; bad |= b;
+            p = nx;
+        }
+        myEntry = entry;
         myExit = (uint32_t)p; myCnt = cnt; myOut = ob; myBad = bad;
     };
     const bool parses = tid < NS;
@@ -383,20 +415,20 @@ __device__ int tile_decode_block(TileSmem<STAGE>& S, const uint8_t* __restrict__
                 const uint32_t rec = lds16(sRec + 2u * k);
                 int cl = (int)(rec & 255u), ol = (int)(rec >> 8);
                 if (cl == 255 || ol == 255) {                    // rare: a long sequence, decode it again
-                    int lit, litPos, ml, off, nx; uint32_t fl;
-                    seq_header<false>(sStg, p, n, lit, litPos, ml, off, nx, fl);
-                    cl = nx - p; ol = lit + ml;
+                    int nx, o; uint32_t b;
+                    seq_next(sStg, p, n, nx, o, b);
+                    cl = nx - p; ol = o;
                 }
                 sts32(sDesc + 4u * idx, (uint32_t)p | ((uint32_t)(op < 65535 ? op : 65535) << 16));
                 idx++; p += cl; op += ol;
             }
         } else {
             while (p < segEnd) {
-                int lit, litPos, ml, off, nx; uint32_t fl;
-                seq_header<false>(sStg, p, n, lit, litPos, ml, off, nx, fl);
+                int nx, o; uint32_t b;
+                seq_next(sStg, p, n, nx, o, b);
                 sts32(sDesc + 4u * idx, (uint32_t)p | ((uint32_t)(op < 65535 ? op : 65535) << 16));
                 idx++;
-                op += lit + ml;
+                op += o;
                 p = nx;
             }
         }

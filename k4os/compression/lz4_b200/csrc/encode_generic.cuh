@@ -19,7 +19,10 @@ namespace k4 {
 
 constexpr int ENC_TABLE_BYTES = 16384;   // LZ4_stream_t hash table, LL.types.cs:18-39
 constexpr int ENC_FLAG_X32 = 0x100;      // `level` bit: reproduce the 32-bit engine (LL32) for inputs >= 65 547 bytes
-constexpr int ENC_TAG_BYTES = 8192;      // one filter byte per u16 slot (encode_tile.cuh)
+#ifndef K4_ENC_TAGS
+#define K4_ENC_TAGS 0
+#endif
+constexpr int ENC_TAG_BYTES = K4_ENC_TAGS ? 8192 : 0;   // one filter byte per u16 slot (encode_tile.cuh)
 constexpr int ENC_SLOT_BYTES = ENC_TABLE_BYTES + ENC_TAG_BYTES;   // shared memory per warp
 
 struct EncCtx {
@@ -215,6 +218,6 @@ __device__ __forceinline__ int codec_encode_warp(const uint8_t* src, int n, uint
     return r <= 0 ? -1 : r;
 }
 
-constexpr int ENC_WARPS_PER_CTA = 9;   // 9 x 24 KiB (table + tags) = 216 KiB: one CTA, nine blocks in flight per SM
+constexpr int ENC_WARPS_PER_CTA = K4_ENC_TAGS ? 9 : 7;   // 9 x 24 KiB (table + tags) = 216 KiB in one CTA, or 2 CTAs x 7 x 16 KiB
 
 }  // namespace k4

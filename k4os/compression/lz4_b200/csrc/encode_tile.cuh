@@ -33,6 +33,7 @@ __device__ __forceinline__ uint32_t lds_u32u(const uint8_t* p) {
 // sets step = searchMatchNb++ >> 6 with searchMatchNb starting at 64 (LL64.fast.cs:159-170): the
 // first advance is 1, advance i >= 1 is (63 + i) >> 6, so the first 65 advances are 1, the next 64 are 2, ...
 __device__ __forceinline__ uint32_t probe_advance(uint32_t q) {
+    if (q <= 64u) return q;                       // the common case: a run shorter than 65 probes
     if (q == 0) return 0;
     const uint32_t c = 63u + q, k = c >> 6;
     return 1u + 32u * k * (k - 1u) + (c - 64u * k) * k;
@@ -41,7 +42,7 @@ __device__ __forceinline__ uint32_t probe_advance(uint32_t q) {
 // The encoder proper.  STAGED: the block sits in shared memory at `sin` (sin[p] == src[p]);
 // otherwise positions are read from global memory through L1 (more blocks in flight per SM).
 // Returns the engine's value: bytes written, 0 when the reference's limitedOutput checks fail.
-template <bool STAGED>
+template <bool STAGED, bool HARD = true>
 __device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* sin, const uint32_t n,
                                 uint8_t* __restrict__ dst, const int cap, const int hardCap, uint16_t* table) {
     const int lane = lane_id();
@@ -56,9 +57,11 @@ __device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* 
     {   // LZ4_initStream: zero the table (LL.tools.cs:235-239); every slot then "holds" position 0
         uint4* t = reinterpret_cast<uint4*>(table);
         for (int i = lane; i < ENC_TABLE_BYTES / 16; i += 32) t[i] = make_uint4(0, 0, 0, 0);
+#if K4_ENC_TAGS
         const uint32_t t0 = n >= 4 ? (((RD32(0) * 2654435761u) >> 11) & 0xFFu) * 0x01010101u : 0u;
         uint4* g = reinterpret_cast<uint4*>(tags);
         for (int i = lane; i < ENC_TAG_BYTES / 16; i += 32) g[i] = make_uint4(t0, t0, t0, t0);
+#endif
         __syncwarp();
     }
 #define RD8(p) (STAGED ? (uint32_t)sin[(p)] : (uint32_t)__ldg(src + (p)))
@@ -88,14 +91,18 @@ __device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* 
             const uint32_t h = valid ? prod >> 19 : (0x10000u + (uint32_t)lane);
             const uint32_t tg = (prod >> 11) & 0xFFu;
             uint32_t cand = valid ? (uint32_t)table[h] : 0u;
+#if K4_ENC_TAGS
             uint32_t ctag = valid ? (uint32_t)tags[h] : 0x100u;
-            if (h == h2) { cand = ip - 2; ctag = tag2; }                          // sees the put(ip-2)
+#else
+            uint32_t ctag = tg;                                                   // no filter: every candidate is fetched
+#endif
+            if (h == h2) { cand = ip - 2; ctag = K4_ENC_TAGS ? tag2 : tg; }       // sees the put(ip-2)
             const unsigned peers = __match_any_sync(FULL, h);
             const unsigned earlier = peers & ((1u << lane) - 1u);
             const int fromLane = earlier ? 31 - __clz(earlier) : lane;
             const uint32_t fwdPos = __shfl_sync(FULL, pos, fromLane);
             const uint32_t fwdTag = __shfl_sync(FULL, tg, fromLane);
-            if (earlier) { cand = fwdPos; ctag = fwdTag; }                        // sees the nearest earlier store
+            if (earlier) { cand = fwdPos; ctag = K4_ENC_TAGS ? fwdTag : tg; }     // sees the nearest earlier store
             bool hit = false;
             if (valid && ctag == tg) hit = RD32(cand) == v;             // :228 (byU16: no distance test)
             const unsigned hits = __ballot_sync(FULL, hit);
@@ -110,9 +117,12 @@ __device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* 
                 const bool doStore = valid && ((1u << lane) & upto) && !(lane < 31 ? later : 0u);
                 if (post) {
                     const unsigned same2 = __ballot_sync(FULL, valid && h == h2) & upto;
-                    if (lane == 0 && !same2) { table[h2] = (uint16_t)(ip - 2); tags[h2] = (uint8_t)tag2; }   // nobody overwrote the put(ip-2)
+                    if (lane == 0 && !same2) {                                    // nobody overwrote the put(ip-2)
+                        table[h2] = (uint16_t)(ip - 2);
+                        if (K4_ENC_TAGS) tags[h2] = (uint8_t)tag2;
+                    }
                 }
-                if (doStore) { table[h] = (uint16_t)pos; tags[h] = (uint8_t)tg; }
+                if (doStore) { table[h] = (uint16_t)pos; if (K4_ENC_TAGS) tags[h] = (uint8_t)tg; }
                 __syncwarp();
             }
             if (f == 32) {                                                        // 32 misses: keep searching
@@ -124,11 +134,13 @@ __device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* 
             uint32_t m = __shfl_sync(FULL, cand, f);
             ip = __shfl_sync(FULL, pos, f);
             if (!zeroLit) {                                                       // step 4: catch-up, :237-242
-                for (;;) {
-                    const bool ok = (ip > anchor + lane) && (m > (uint32_t)lane) &&
-                                    (RD8(ip - 1 - lane) == RD8(m - 1 - lane));
+                // eight lanes first: a catch-up is rarely longer, and lanes that do not take part issue no load
+                for (int width = 8;; width = 32) {
+                    const bool part = lane < width;
+                    const bool ok = !part || ((ip > anchor + lane) && (m > (uint32_t)lane) &&
+                                              (RD8(ip - 1 - lane) == RD8(m - 1 - lane)));
                     const unsigned bad = __ballot_sync(FULL, !ok);
-                    const int c = bad ? __ffs(bad) - 1 : 32;
+                    const int c = bad ? __ffs(bad) - 1 : width;
                     ip -= c; m -= c;
                     if (bad) break;
                 }
@@ -137,26 +149,30 @@ __device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* 
             const uint32_t lit = ip - anchor;
             if (!zeroLit && limited && (int64_t)op + 1 + lit + 8 + lit / 255 > olimit) return 0;   // :246-251
             uint32_t mc = 0;
-            {   // LZ4_count(ip+4, m+4, matchlimit), 4 bytes per lane, :328
-                uint32_t a = ip + MINMATCH + 4u * lane, bb = m + MINMATCH + 4u * lane;
-                for (;;) {
+            {   // LZ4_count(ip+4, m+4, matchlimit), 4 bytes per lane, :328; the first round looks at 32 bytes
+                // (eight lanes: half of all matches end there and the other lanes' lines are not fetched)
+                uint32_t a0 = ip + MINMATCH, b0 = m + MINMATCH;
+                for (int width = 8;; width = 32) {
+                    const uint32_t a = a0 + 4u * lane, bb = b0 + 4u * lane;
+                    const bool part = lane < width;
                     const int room = (int)mlim - (int)a;                          // bytes of this lane below matchlimit
-                    const uint32_t x = room > 0 ? (RD32(a) ^ RD32(bb)) : 0u;
+                    const uint32_t x = (part && room > 0) ? (RD32(a) ^ RD32(bb)) : 0u;
                     int eq = x ? ((__ffs(x) - 1) >> 3) : 4;
                     if (eq > room) eq = room < 0 ? 0 : room;
+                    if (!part) eq = 4;
                     const unsigned stop = __ballot_sync(FULL, eq < 4);
                     if (stop) {
                         const int s = __ffs(stop) - 1;
                         mc += 4u * s + (uint32_t)__shfl_sync(FULL, eq, s);
                         break;
                     }
-                    mc += 128; a += 128; bb += 128;
+                    mc += 4u * width; a0 += 4u * width; b0 += 4u * width;
                 }
             }
             const uint32_t hdr = run_header_size(lit);
             const uint32_t afterOff = op + hdr + lit + 2;
             if (limited && (int64_t)afterOff + 6 + (mc + 240) / 255 > olimit) return 0;   // :332-362
-            if ((int64_t)afterOff + (mc >= 15 ? (mc - 15) / 255 + 1 : 0) > hard) return 0;
+            if (HARD && (int64_t)afterOff + (mc >= 15 ? (mc - 15) / 255 + 1 : 0) > hard) return 0;
             // emit: token, literal length bytes, literals, offset, match length bytes
             {
                 const uint32_t mlTok = mc >= 15 ? 15u : mc;
@@ -189,7 +205,7 @@ __device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* 
         const uint32_t run = n - anchor;
         if (limited && (int64_t)op + run + 1 + (run + 255 - 15) / 255 > olimit) return 0;
         const uint32_t hdr = run_header_size(run);
-        if ((int64_t)op + hdr + run > hard) return 0;
+        if (HARD && (int64_t)op + hdr + run > hard) return 0;
         if (lane == 0) write_run_header(dst, op, run);
         op += hdr;
         for (uint32_t i = lane; i < run; i += 32) dst[op + i] = RD8(anchor + i);
@@ -222,7 +238,7 @@ encode_spec_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restric
     if (level >= 3) { if (lane == 0) outLen[b] = -2; return; }
     int r;
     if (n_ >= LIMIT_64K) r = encode_block_warp(src, n_, dst, cap, 0x7fffffff, table, enforce32);
-    else r = encode_spec_warp<false>(src, nullptr, (uint32_t)n_, dst, cap, 0x7fffffff, table);
+    else r = encode_spec_warp<false, false>(src, nullptr, (uint32_t)n_, dst, cap, 0x7fffffff, table);
     if (lane == 0) outLen[b] = r <= 0 ? -1 : r;
 }
 

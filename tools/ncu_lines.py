@@ -15,7 +15,7 @@ rep, kname = sys.argv[1], sys.argv[2]
 lib = sys.argv[3] if len(sys.argv) > 3 else "k4os/compression/lz4_b200/libk4lz4.so"
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 60
 
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + (["--kernel-name", "regex:" + os.environ["NCU_KERNEL"]] if os.environ.get("NCU_KERNEL") else []), capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hi = [i for i, r in enumerate(rows) if "Instructions Executed" in r][0]
 hdr = rows[hi]
