@@ -406,6 +406,15 @@ int enqueue_chunk(Op op, const HostArgs& a, Slot& s, int64_t b0, int64_t b1) {
     return K4LZ4_OK;
 }
 
+// blocks the encoder processes at once on `dev`: SMs x CTAs per SM x warps per CTA
+int64_t enc_wave_blocks(int dev) {
+    static int sms[64] = {0};
+    if (dev < 0 || dev >= 64) return 1;
+    if (!sms[dev]) { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) v = 0; sms[dev] = v > 0 ? v : -1; }
+    const int ctasPerSm = (227 * 1024) / (k4::ENC_WARPS_PER_CTA * k4::ENC_SLOT_BYTES + 1024);
+    return sms[dev] > 0 ? (int64_t)sms[dev] * (ctasPerSm > 0 ? ctasPerSm : 1) * k4::ENC_WARPS_PER_CTA : 1;
+}
+
 // One device, blocks [b0, b1): chunked + double-buffered (H2D/kernel/D2H of chunk c overlap
 // the host-side scatter of chunk c-1 and the copies of chunk c+1 on the other stream).
 int run_host_slice(Op op, const HostArgs& a, int64_t b0, int64_t b1, int dev) {
@@ -425,10 +434,19 @@ int run_host_slice(Op op, const HostArgs& a, int64_t b0, int64_t b1, int dev) {
     // D2H) of chunk c-1 and stage 3 (host scatter, if needed) of chunk c-2
     while (i < b1) {
         int64_t bytes = 0, j = i;
-        while (j < b1 && (j == i || bytes + src_size(a, j) + dst_room(op, a, j) <= CHUNK_BYTES)) {
+        // The encoder keeps one warp busy per block for milliseconds (a serial chain per block): a chunk
+        // should fill the GPU's warp slots a whole number of times, else its kernel ends on a half-empty
+        // wave.  Encode / pickle chunks therefore hold a multiple of `wave` blocks (up to 768 MiB).
+        const bool encLike = op == OP_ENCODE || op == OP_PICKLE || op == OP_PICKLEW;
+        const int64_t limit = encLike ? 4 * CHUNK_BYTES : CHUNK_BYTES;
+        const int64_t wave = encLike ? enc_wave_blocks(dev) : 1;
+        int64_t jWave = -1;
+        while (j < b1 && (j == i || bytes + src_size(a, j) + dst_room(op, a, j) <= limit)) {
             bytes += src_size(a, j) + dst_room(op, a, j);
             j++;
+            if (wave > 1 && (j - i) % wave == 0) jWave = j;
         }
+        if (jWave > i && j < b1) j = jWave;                    // not the last chunk: cut at a wave boundary
         Slot& s = ctx->slot[c % 3];
         if ((rc = stage3_slot(op, a, s)) != K4LZ4_OK) break;
         if ((rc = enqueue_chunk(op, a, s, i, j)) != K4LZ4_OK) break;

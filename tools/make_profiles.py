@@ -1,0 +1,127 @@
+"""tools/make_profiles.py -- turns the ncu reports of a GPU session (gpurun_out/) into the committed
+text summaries under profiles/ (run here, without a GPU; the library on disk must be the profiled build).
+    python tools/make_profiles.py <step.ncu-rep> <enc.ncu-rep> <launches.csv> <round-tag>
+"""
+import csv
+import json
+import os
+import subprocess
+import sys
+
+step_rep, enc_rep, launches_csv, tag = sys.argv[1:5]
+LIB = "k4os/compression/lz4_b200/libk4lz4.so"
+KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
+        'launch__shared_mem_per_block_dynamic', 'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_registers',
+        'smsp__thread_inst_executed_per_inst_executed.ratio', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum',
+        'l1tex__t_sector_hit_rate.pct', 'lts__t_sectors_srcunit_tex_op_read.sum', 'lts__t_sector_hit_rate.pct']
+
+
+def raw(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    return [{h: (r[i], units[i]) for i, h in enumerate(hdr)} for r in rows[2:]]
+
+
+def fmt(d):
+    return "\n".join(f"  {k:70s} {d[k][0]} {d[k][1]}" for k in ['Kernel Name', 'Grid Size', 'Block Size'] + KEYS if k in d)
+
+
+def lines(rep, kname, envk=None, top=40):
+    env = dict(os.environ)
+    if envk:
+        env['NCU_KERNEL'] = envk
+    return subprocess.run(["python", "tools/ncu_lines.py", rep, kname, LIB, str(top)], capture_output=True, text=True, env=env).stdout
+
+
+def num(d, k):
+    v, u = d[k]
+    v = float(v.replace(',', ''))
+    return v * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1}.get(u, 1)
+
+
+ks = raw(step_rep)
+dec = [d for d in ks if d['Kernel Name'][0].startswith('decode_tile_kernel')][0]
+big = [d for d in ks if d['Kernel Name'][0].startswith('decode_tile_big')]
+rest = [d for d in ks if d['Kernel Name'][0].startswith('decode_rest')]
+encs = [d for d in ks if d['Kernel Name'][0].startswith('encode_spec')]
+enc8k = raw(enc_rep)[0]
+dr, dw = num(dec, 'dram__bytes_read.sum'), num(dec, 'dram__bytes_write.sum')
+inst = float(dec['smsp__inst_executed.sum'][0].replace(',', ''))
+nblk = int(dec['Grid Size'][0].strip('()').split(',')[0])
+open(f'profiles/ncu_{tag}_decode_summary.txt', 'w').write(f"""# ncu --set full --import-source on --clock-control none -k regex:"decode_tile_kernel|decode_tile_big|decode_rest|encode_spec" -s <warm-up> -c <n>
+#   python bench.py --steps 1 --warmup 3 --no-cpu-baseline        (B200; report under gpurun_out/, not committed)
+# The decode pass of the bench step = three launches (tile kernel + two follow-ups that read their work list's length on the device).
+
+== launch 1: the tile kernel, configs[1] ({nblk} blocks of the reference datagen workload)
+{fmt(dec)}
+
+   measured DRAM traffic {dr/1e9:.3f} GB read + {dw/1e9:.3f} GB written = {(dr+dw)/1e9:.3f} GB per launch; algorithmic bytes per launch
+   (compressed read + raw written) are printed by bench.py as roofline.algorithmic_bytes_per_launch (6 451 287 933 for this config):
+   ratio {(dr+dw)/6451287933:.3f} -- the compressed stream is read once, the raw block written once, nothing else moves
+   (round 1: 10.1 GB per step = 1.57 x, plus a 4.4 GB scratch allocation).
+   {inst/1e9:.2f} G warp instructions / {nblk} blocks = {inst/nblk/1e3:.0f} K per block.  The kernel is bound by the per-block LATENCY
+   (two blocks resident per SM, shared memory): see DESIGN.md section 7.
+
+== launch 2: big-stage variant
+{fmt(big[0]) if big else '  (not captured)'}
+
+== launch 3: exact warp-per-block decoder
+{fmt(rest[0]) if rest else '  (not captured)'}
+
+== per-source-line hot spots of the tile kernel (share of executed warp instructions / of stall samples / average active lanes;
+   SASS aggregated through nvdisasm -g line info by tools/ncu_lines.py; line numbers are those of the committed decode_tile.cuh)
+{lines(step_rep, 'decode_tile_kernelE', '^decode_tile_kernel', 45)}
+""")
+e = encs[0] if encs else None
+open(f'profiles/ncu_{tag}_encode_summary.txt', 'w').write(f"""# (a) the encode pass of the bench step (65 536 blocks of the configs[2] workload), same ncu command as ncu_{tag}_decode_summary.txt
+{fmt(e) if e else '  (not captured)'}
+
+# (b) ncu --set full --import-source on --clock-control none -k regex:encode_spec_kernel -c 1
+#   python tools/dbench.py --blocks 8192 --data datagen --mp 550 --reps 1 --what encode     (1/8 of the pass; source counters)
+{fmt(enc8k)}
+
+   One warp per block, 14 blocks in flight per SM (two CTAs of 7 warps x 16 KiB hash table).  The chain per sequence is
+   serial (the reference's single-slot table history); ~11 cycles per dependent instruction, ~290 warp instructions per
+   sequence.  Global loads are dominated by the 32 speculative candidate reads per probe batch (L1 hit ~50 %, L2 hit > 90 %).
+   An 8-bit tag filter in front of the candidate reads (-DK4_ENC_TAGS=1: 24 KiB per warp, 9 blocks per SM) removes most
+   of them but measured SLOWER (17.8 vs 23.8 GB/s on this workload): occupancy, not load bandwidth, is what the chains need.
+
+== per-source-line hot spots of (b)
+{lines(enc_rep, 'encode_spec_kernelE', None, 40)}
+""")
+tr = {"decode_bytes_per_launch": int(dr + dw),
+      "decode_split": {"k4::decode_tile_kernel": {"dram_read": int(dr), "dram_write": int(dw)},
+                       "k4::decode_tile_big_kernel": "empty work list in the bench's decode pass (every block fits the small stage)",
+                       "k4::decode_rest_kernel": "empty work list"},
+      "encode_bytes_per_launch": int(num(e, 'dram__bytes_read.sum') + num(e, 'dram__bytes_write.sum')) if e else
+      int((num(enc8k, 'dram__bytes_read.sum') + num(enc8k, 'dram__bytes_write.sum')) * 8),
+      "source": f"profiles/ncu_{tag}_decode_summary.txt, profiles/ncu_{tag}_encode_summary.txt (ncu --set full of `python bench.py --steps 1 --warmup 3 --no-cpu-baseline`)"}
+json.dump(tr, open('profiles/traffic.json', 'w'), indent=1)
+
+# launch list: per-kernel totals of the same command
+rows = [r for r in csv.reader(open(launches_csv)) if len(r) > 5]
+hdr = rows[0]
+ki, vi = hdr.index('Kernel Name'), hdr.index('Metric Value')
+agg = {}
+order = []
+for r in rows[1:]:
+    try:
+        v = float(r[vi].replace(',', ''))
+    except ValueError:
+        continue
+    k = r[ki].split('(')[0]
+    if k not in agg:
+        order.append(k)
+    agg.setdefault(k, []).append(v)
+tot = sum(sum(v) for v in agg.values())
+with open(f'profiles/launches_{tag}.csv', 'w') as f:
+    f.write("kernel,launches,total_ms,mean_ms,share_of_listed_time\n")
+    for k in order:
+        v = agg[k]
+        f.write(f"{k},{len(v)},{sum(v)/1e6:.4f},{sum(v)/len(v)/1e6:.4f},{sum(v)/tot:.4f}\n")
+print(open(f'profiles/launches_{tag}.csv').read())
