@@ -273,19 +273,23 @@ __device__ __forceinline__ void warp_copy_match_smem(uint32_t d, const int off, 
     for (int i = lane; i < len; i += 32) sts8(d + i, lds8(s + (i % off)));
 }
 
-// one lane, source and destination do not overlap: four bytes in flight per trip
-__device__ __forceinline__ void lane_copy(const uint32_t d, const uint32_t s, const int len) {
-    int j = 0;
-    for (; j + 4 <= len; j += 4) {
-        const uint32_t v0 = lds8(s + j), v1 = lds8(s + j + 1), v2 = lds8(s + j + 2), v3 = lds8(s + j + 3);
-        sts8(d + j, v0); sts8(d + j + 1, v1); sts8(d + j + 2, v2); sts8(d + j + 3, v3);
+// Lane-parallel copies of short runs, called by ALL lanes of a warp (len = 0 for lanes without work).
+// The warp walks the runs in tiers of eight bytes; inside a tier every lane issues its (predicated)
+// loads back to back and only then its stores, so a tier costs one shared-memory round trip instead of
+// one per group of bytes (measured: the byte-group loop was the longest serial chain of a step).
+// `ovl` lanes (LZ77 copy whose source runs into its destination) are done byte by byte afterwards.
+__device__ __forceinline__ void lanes_copy(const uint32_t d, const uint32_t s, const int len, const bool ovl) {
+    const int plain = ovl ? 0 : len;
+    const int top = __reduce_max_sync(FULL, plain);
+    for (int base = 0; base < top; base += 8) {
+        const int left = plain - base;
+        uint32_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) if (j < left) v[j] = lds8(s + base + j);
+#pragma unroll
+        for (int j = 0; j < 8; j++) if (j < left) sts8(d + base + j, v[j]);
     }
-    for (; j < len; j++) sts8(d + j, lds8(s + j));
-}
-// one lane, LZ77 semantics (the source may run into the destination): strictly byte by byte then
-__device__ __forceinline__ void lane_copy_match(const uint32_t d, const int off, const int len) {
-    if (off >= len) { lane_copy(d, d - (uint32_t)off, len); return; }
-    for (int j = 0; j < len; j++) sts8(d + j, lds8(d + j - (uint32_t)off));
+    if (ovl) for (int j = 0; j < len; j++) sts8(d + j, lds8(s + j));
 }
 
 // ---- the tile decoder ---------------------------------------------------------------------------
@@ -477,13 +481,13 @@ __device__ int tile_decode_block(TileSmem<STAGE>& S, const uint8_t* __restrict__
         const bool farM = ml > 0 && !nearM;
 
         // literals, then far matches: short runs by the owning lane, long ones by the whole warp
-        if (lit > 0 && lit <= DT_LSHORT) lane_copy(sT + (uint32_t)op, sStg + (uint32_t)litPos, lit);
+        lanes_copy(sT + (uint32_t)op, sStg + (uint32_t)litPos, lit <= DT_LSHORT ? lit : 0, false);
         for (unsigned m = __ballot_sync(FULL, lit > DT_LSHORT); m; m &= m - 1) {
             const int l = __ffs(m) - 1;
             warp_copy(sT + (uint32_t)__shfl_sync(FULL, op, l), sStg + (uint32_t)__shfl_sync(FULL, litPos, l), __shfl_sync(FULL, lit, l), lane);
         }
         DT_PROF(6);
-        if (farM && ml <= DT_LSHORT) lane_copy_match(sT + (uint32_t)d, off, ml);
+        lanes_copy(sT + (uint32_t)d, sT + (uint32_t)a, farM && ml <= DT_LSHORT ? ml : 0, off < ml);
         for (unsigned m = __ballot_sync(FULL, farM && ml > DT_LSHORT); m; m &= m - 1) {
             const int l = __ffs(m) - 1;
             warp_copy_match_smem(sT + (uint32_t)__shfl_sync(FULL, d, l), __shfl_sync(FULL, off, l), __shfl_sync(FULL, ml, l), lane);
@@ -539,7 +543,7 @@ __device__ int tile_decode_block(TileSmem<STAGE>& S, const uint8_t* __restrict__
                             go = lo >= hi;
                         }
                         __threadfence_block();                   // bytes behind the cleared flags
-                        if (go && nml <= DT_LSHORT) lane_copy_match(sT + (uint32_t)nd, noff, nml);
+                        lanes_copy(sT + (uint32_t)nd, sT + (uint32_t)(nd - noff), go && nml <= DT_LSHORT ? nml : 0, noff < nml);
                         for (unsigned m = __ballot_sync(FULL, go && nml > DT_LSHORT); m; m &= m - 1) {
                             const int l = __ffs(m) - 1;
                             warp_copy_match_smem(sT + (uint32_t)__shfl_sync(FULL, nd, l), __shfl_sync(FULL, noff, l), __shfl_sync(FULL, nml, l), lane);
@@ -716,7 +720,7 @@ inline DecodeDev* decode_dev(int dev) {
             props.location.id = dev;
             e = cudaMemPoolCreate(&d->pool, &props);
             if (e == cudaSuccess) {
-                unsigned long long keep = 64ull << 20;          // cache up to 64 MiB of work lists
+                unsigned long long keep = 256ull << 20;         // cache up to 256 MiB of work lists and encoder tables
                 cudaMemPoolSetAttribute(d->pool, cudaMemPoolAttrReleaseThreshold, &keep);
             }
         }

@@ -42,12 +42,16 @@ __device__ __forceinline__ uint32_t probe_advance(uint32_t q) {
 // The encoder proper.  STAGED: the block sits in shared memory at `sin` (sin[p] == src[p]);
 // otherwise positions are read from global memory through L1 (more blocks in flight per SM).
 // Returns the engine's value: bytes written, 0 when the reference's limitedOutput checks fail.
-template <bool STAGED, bool HARD = true>
+template <bool STAGED, bool HARD = true, bool GTAB = false>
 __device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* sin, const uint32_t n,
                                 uint8_t* __restrict__ dst, const int cap, const int hardCap, uint16_t* table) {
     const int lane = lane_id();
     const int64_t hard = hardCap;       // physical write bound (pickler, see pickle.cuh); 0x7fffffff otherwise
 #define RD32(p) (STAGED ? lds_u32u(sin + (p)) : ldg_u32u(src + (p)))
+    // GTAB: the table lives in global memory; its accesses go to L2 (.cg) so that the little L1 left
+    // beside 224 KiB of shared memory keeps the input windows of all warps of the SM
+#define TGET(h) (GTAB ? (uint32_t)__ldcg(table + (h)) : (uint32_t)table[(h)])
+#define TPUT(h, v) do { if (GTAB) __stcg(table + (h), (uint16_t)(v)); else table[(h)] = (uint16_t)(v); } while (0)
     // Tag filter.  Next to every 16-bit slot sits an 8-bit tag: bits 11..18 of the same product whose
     // bits 19..31 are the hash, taken from the 4 bytes AT the stored position.  Equal 4-byte values
     // have equal tags, so a probe only has to fetch its candidate's bytes (a scattered global load,
@@ -56,7 +60,9 @@ __device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* 
     uint8_t* const tags = reinterpret_cast<uint8_t*>(table) + ENC_TABLE_BYTES;
     {   // LZ4_initStream: zero the table (LL.tools.cs:235-239); every slot then "holds" position 0
         uint4* t = reinterpret_cast<uint4*>(table);
-        for (int i = lane; i < ENC_TABLE_BYTES / 16; i += 32) t[i] = make_uint4(0, 0, 0, 0);
+        for (int i = lane; i < ENC_TABLE_BYTES / 16; i += 32) {
+            if (GTAB) __stcg(t + i, make_uint4(0, 0, 0, 0)); else t[i] = make_uint4(0, 0, 0, 0);
+        }
 #if K4_ENC_TAGS
         const uint32_t t0 = n >= 4 ? (((RD32(0) * 2654435761u) >> 11) & 0xFFu) * 0x01010101u : 0u;
         uint4* g = reinterpret_cast<uint4*>(tags);
@@ -71,7 +77,7 @@ __device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* 
 
     if (n >= (uint32_t)MINLENGTH) {                                               // :117
         const uint32_t mfl1 = n - MFLIMIT + 1, mlim = n - LASTLITERALS;           // :70-71
-        if (lane == 0) table[hash4(RD32(0), 13)] = 0;                       // :120
+        if (lane == 0) TPUT(hash4(RD32(0), 13), 0);                       // :120
         __syncwarp();
         ip = 1;
         bool post = false;              // lane 0 of the next batch is the post-match probe at ip
@@ -90,7 +96,7 @@ __device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* 
             const uint32_t prod = v * 2654435761u;
             const uint32_t h = valid ? prod >> 19 : (0x10000u + (uint32_t)lane);
             const uint32_t tg = (prod >> 11) & 0xFFu;
-            uint32_t cand = valid ? (uint32_t)table[h] : 0u;
+            uint32_t cand = valid ? TGET(h) : 0u;
 #if K4_ENC_TAGS
             uint32_t ctag = valid ? (uint32_t)tags[h] : 0x100u;
 #else
@@ -118,11 +124,11 @@ __device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* 
                 if (post) {
                     const unsigned same2 = __ballot_sync(FULL, valid && h == h2) & upto;
                     if (lane == 0 && !same2) {                                    // nobody overwrote the put(ip-2)
-                        table[h2] = (uint16_t)(ip - 2);
+                        TPUT(h2, ip - 2);
                         if (K4_ENC_TAGS) tags[h2] = (uint8_t)tag2;
                     }
                 }
-                if (doStore) { table[h] = (uint16_t)pos; if (K4_ENC_TAGS) tags[h] = (uint8_t)tg; }
+                if (doStore) { TPUT(h, pos); if (K4_ENC_TAGS) tags[h] = (uint8_t)tg; }
                 __syncwarp();
             }
             if (f == 32) {                                                        // 32 misses: keep searching
@@ -213,33 +219,52 @@ __device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* 
         return (int)op;
     }
 #undef RD32
+#undef TGET
+#undef TPUT
 #undef RD8
 }
 
-// Global-memory variant: ENC_WARPS_PER_CTA blocks per CTA, only the 16 KiB tables in shared memory.
-__global__ void __launch_bounds__(ENC_WARPS_PER_CTA * 32)
+// Persistent kernel, one warp per block at a time; blocks are handed out by a device counter.  Input and
+// output stay in global memory (more blocks in flight per SM than staging would allow); warps
+// 0..ENC_WARPS_PER_CTA-1 keep their hash table in shared memory, the ENC_GWARPS warps after them in
+// the `gtab` workspace (one 16 KiB slot per such warp of the grid).
+__global__ void __launch_bounds__(ENC_CTA_WARPS * 32, ENC_CTAS_PER_SM)
 encode_spec_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restrict__ srcOff,
                    const int32_t* __restrict__ srcLen, uint8_t* __restrict__ dstBase,
                    const int64_t* __restrict__ dstOff, const int32_t* __restrict__ dstCap,
-                   int32_t* __restrict__ outLen, int nBlocks, int level) {
+                   int32_t* __restrict__ outLen, int nBlocks, int level,
+                   uint32_t* __restrict__ nextBlock, uint8_t* __restrict__ gtab) {
     extern __shared__ __align__(128) uint8_t smem_encs[];
     const int wInCta = threadIdx.x >> 5;
-    const int b = blockIdx.x * ENC_WARPS_PER_CTA + wInCta;
     const int lane = lane_id();
-    if (b >= nBlocks) return;
-    uint16_t* table = reinterpret_cast<uint16_t*>(smem_encs + wInCta * ENC_SLOT_BYTES);
-    const int n_ = srcLen[b];
-    const uint8_t* __restrict__ src = srcBase + srcOff[b];
-    uint8_t* __restrict__ dst = dstBase + dstOff[b];
-    const int cap = dstCap[b];
-    if (n_ <= 0) { if (lane == 0) outLen[b] = 0; return; }
+    const bool inShared = wInCta < ENC_WARPS_PER_CTA;
+    uint16_t* const stable = reinterpret_cast<uint16_t*>(smem_encs + (inShared ? wInCta : 0) * ENC_SLOT_BYTES);
+    uint16_t* const gtable = reinterpret_cast<uint16_t*>(
+        gtab + ((size_t)blockIdx.x * ENC_GWARPS + (size_t)(inShared ? 0 : wInCta - ENC_WARPS_PER_CTA)) * ENC_SLOT_BYTES);
     const bool enforce32 = (level & ENC_FLAG_X32) != 0;   // LL.Enforce32 (LL.tools.cs:29): hash4 for the byU32 table
     level &= 0xFF;
-    if (level >= 3) { if (lane == 0) outLen[b] = -2; return; }
-    int r;
-    if (n_ >= LIMIT_64K) r = encode_block_warp(src, n_, dst, cap, 0x7fffffff, table, enforce32);
-    else r = encode_spec_warp<false, false>(src, nullptr, (uint32_t)n_, dst, cap, 0x7fffffff, table);
-    if (lane == 0) outLen[b] = r <= 0 ? -1 : r;
+    for (;;) {
+        int b = 0;
+        if (lane == 0) {
+            // the slower global-table warps leave the last blocks to the shared-memory warps (shorter tail)
+            if (!inShared && (int)*(volatile uint32_t*)nextBlock >= nBlocks - K4_ENC_TAIL * (int)gridDim.x * ENC_WARPS_PER_CTA) b = nBlocks;
+            else b = (int)atomicAdd(nextBlock, 1u);
+        }
+        b = __shfl_sync(FULL, b, 0);
+        if (b >= nBlocks) return;
+        const int n_ = srcLen[b];
+        const uint8_t* __restrict__ src = srcBase + srcOff[b];
+        uint8_t* __restrict__ dst = dstBase + dstOff[b];
+        const int cap = dstCap[b];
+        if (n_ <= 0) { if (lane == 0) outLen[b] = 0; continue; }
+        if (level >= 3) { if (lane == 0) outLen[b] = -2; continue; }
+        int r;
+        if (n_ >= LIMIT_64K) r = encode_block_warp(src, n_, dst, cap, 0x7fffffff, inShared ? (void*)stable : (void*)gtable, enforce32);
+        else if (inShared) r = encode_spec_warp<false, false>(src, nullptr, (uint32_t)n_, dst, cap, 0x7fffffff, stable);
+        else r = encode_spec_warp<false, false, true>(src, nullptr, (uint32_t)n_, dst, cap, 0x7fffffff, gtable);
+        if (lane == 0) outLen[b] = r <= 0 ? -1 : r;
+        __syncwarp();
+    }
 }
 
 }  // namespace k4

@@ -83,6 +83,33 @@ void set_func_attrs(int dev) {
     });
 }
 
+// Enqueues the persistent block encoder: one grid-filling launch; its workspace (block counter + the
+// global-memory hash tables of the ENC_GWARPS warps per CTA) comes from the private stream-ordered pool.
+cudaError_t encode_launch(const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen,
+                          uint8_t* dstBase, const int64_t* dstOff, const int32_t* dstCap,
+                          int32_t* outLen, int n, int level, cudaStream_t st) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    k4::DecodeDev* D = k4::decode_dev(dev);
+    if (!D || D->err != cudaSuccess) return D ? D->err : cudaErrorInvalidDevice;
+    const int want = (n + k4::ENC_CTA_WARPS - 1) / k4::ENC_CTA_WARPS;
+    const int full = D->sms * k4::ENC_CTAS_PER_SM;
+    const int ctas = want < full ? want : full;
+    const size_t tabBytes = (size_t)ctas * k4::ENC_GWARPS * k4::ENC_SLOT_BYTES;
+    uint8_t* ws = nullptr;
+    cudaError_t e = cudaMallocFromPoolAsync((void**)&ws, 256 + tabBytes, D->pool, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(ws, 0, 4, st);
+    if (e == cudaSuccess) {
+        k4::encode_spec_kernel<<<ctas, k4::ENC_CTA_WARPS * 32, k4::ENC_WARPS_PER_CTA * k4::ENC_SLOT_BYTES, st>>>(
+            srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, n, level,
+            reinterpret_cast<uint32_t*>(ws), ws + 256);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(ws, st);
+    return e;
+}
+
 struct DevArgs {
     const uint8_t* srcBase; const int64_t* srcOff; const int32_t* srcLen;
     uint8_t* dstBase; const int64_t* dstOff; const int32_t* dstCap;
@@ -96,10 +123,9 @@ cudaError_t launch_op(Op op, const DevArgs& a, cudaStream_t st) {
     set_func_attrs(dev);
     switch (op) {
     case OP_ENCODE: {
-        const int ctas = (a.n + k4::ENC_WARPS_PER_CTA - 1) / k4::ENC_WARPS_PER_CTA;
-        k4::encode_spec_kernel<<<ctas, k4::ENC_WARPS_PER_CTA * 32,
-                                 k4::ENC_WARPS_PER_CTA * k4::ENC_SLOT_BYTES, st>>>(
-            a.srcBase, a.srcOff, a.srcLen, a.dstBase, a.dstOff, a.dstCap, a.outLen, a.n, a.level);
+        const cudaError_t ee = encode_launch(a.srcBase, a.srcOff, a.srcLen, a.dstBase, a.dstOff, a.dstCap,
+                                             a.outLen, a.n, a.level, st);
+        if (ee != cudaSuccess) { (void)cudaGetLastError(); return ee; }
         g_launches++;
         break;
     }
@@ -411,8 +437,7 @@ int64_t enc_wave_blocks(int dev) {
     static int sms[64] = {0};
     if (dev < 0 || dev >= 64) return 1;
     if (!sms[dev]) { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) v = 0; sms[dev] = v > 0 ? v : -1; }
-    const int ctasPerSm = (227 * 1024) / (k4::ENC_WARPS_PER_CTA * k4::ENC_SLOT_BYTES + 1024);
-    return sms[dev] > 0 ? (int64_t)sms[dev] * (ctasPerSm > 0 ? ctasPerSm : 1) * k4::ENC_WARPS_PER_CTA : 1;
+    return sms[dev] > 0 ? (int64_t)sms[dev] * k4::ENC_CTAS_PER_SM * k4::ENC_CTA_WARPS : 1;
 }
 
 // One device, blocks [b0, b1): chunked + double-buffered (H2D/kernel/D2H of chunk c overlap
