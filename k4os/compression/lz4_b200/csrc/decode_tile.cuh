@@ -35,6 +35,7 @@
 // Reference semantics: /root/reference/src/K4os.Compression.LZ4/Engine/x64/LL64.dec.cs:124-477,
 // Engine/LL.tools.cs:165-193 (LZ4_readVLE), LZ4Codec.cs:104-115.
 #pragma once
+#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
@@ -698,6 +699,8 @@ struct DecodeDev {
     cudaMemPool_t pool = nullptr;
     int sms = 0;
     cudaError_t err = cudaSuccess;
+    cudaStream_t helper[4] = {nullptr, nullptr, nullptr, nullptr};   // side streams of the encoder (encode_launch)
+    std::atomic<unsigned> nextHelper{0};
 };
 
 inline DecodeDev* decode_dev(int dev) {
@@ -724,6 +727,7 @@ inline DecodeDev* decode_dev(int dev) {
                 cudaMemPoolSetAttribute(d->pool, cudaMemPoolAttrReleaseThreshold, &keep);
             }
         }
+        for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&d->helper[i], cudaStreamNonBlocking);
         d->err = e;
     });
     return d;

@@ -218,18 +218,15 @@ __device__ __forceinline__ int codec_encode_warp(const uint8_t* src, int n, uint
     return r <= 0 ? -1 : r;
 }
 
-constexpr int ENC_WARPS_PER_CTA = K4_ENC_TAGS ? 9 : 7;   // 9 x 24 KiB (table + tags) = 216 KiB in one CTA, or 2 CTAs x 7 x 16 KiB
-// encode_spec_kernel: next to the ENC_WARPS_PER_CTA warps whose table lives in shared memory, every CTA
-// carries ENC_GWARPS warps whose 16 KiB table lives in global memory (L2-resident workspace).  They are
-// slower per block, but they use issue slots and registers the shared-memory warps leave idle.
-#ifndef K4_ENC_GWARPS
-#define K4_ENC_GWARPS 4
+constexpr int ENC_WARPS_PER_CTA = K4_ENC_TAGS ? 9 : 7;   // pickle_kernel: 2 CTAs x 7 warps x 16 KiB of tables fill the SM
+// encode_spec_kernel / encode_spec_gtab_kernel (one warp per CTA, see encode_tile.cuh): resident warps per SM
+#ifndef K4_ENC_SM_WARPS
+#define K4_ENC_SM_WARPS 7       // shared-memory tables: 7 x (16 KiB + 1 KiB the hardware reserves per CTA); the rest of the 256 KiB stays L1
 #endif
-#ifndef K4_ENC_TAIL
-#define K4_ENC_TAIL 1
+#ifndef K4_ENC_GM_WARPS
+#define K4_ENC_GM_WARPS 25      // global-memory tables (sweep in DESIGN.md 4.2)
 #endif
-constexpr int ENC_GWARPS = K4_ENC_GWARPS;
-constexpr int ENC_CTA_WARPS = ENC_WARPS_PER_CTA + ENC_GWARPS;
-constexpr int ENC_CTAS_PER_SM = (227 * 1024) / (ENC_WARPS_PER_CTA * ENC_SLOT_BYTES + 1024);
+constexpr int ENC_SM_WARPS = K4_ENC_SM_WARPS;
+constexpr int ENC_GM_WARPS = K4_ENC_GM_WARPS;
 
 }  // namespace k4

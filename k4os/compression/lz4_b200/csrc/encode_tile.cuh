@@ -50,8 +50,11 @@ __device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* 
 #define RD32(p) (STAGED ? lds_u32u(sin + (p)) : ldg_u32u(src + (p)))
     // GTAB: the table lives in global memory; its accesses go to L2 (.cg) so that the little L1 left
     // beside 224 KiB of shared memory keeps the input windows of all warps of the SM
-#define TGET(h) (GTAB ? (uint32_t)__ldcg(table + (h)) : (uint32_t)table[(h)])
-#define TPUT(h, v) do { if (GTAB) __stcg(table + (h), (uint16_t)(v)); else table[(h)] = (uint16_t)(v); } while (0)
+#ifndef K4_ENC_GTAB_L1
+#define K4_ENC_GTAB_L1 0
+#endif
+#define TGET(h) ((GTAB && !K4_ENC_GTAB_L1) ? (uint32_t)__ldcg(table + (h)) : (uint32_t)table[(h)])
+#define TPUT(h, v) do { if (GTAB && !K4_ENC_GTAB_L1) __stcg(table + (h), (uint16_t)(v)); else table[(h)] = (uint16_t)(v); } while (0)
     // Tag filter.  Next to every 16-bit slot sits an 8-bit tag: bits 11..18 of the same product whose
     // bits 19..31 are the hash, taken from the 4 bytes AT the stored position.  Equal 4-byte values
     // have equal tags, so a probe only has to fetch its candidate's bytes (a scattered global load,
@@ -224,30 +227,27 @@ __device__ int encode_spec_warp(const uint8_t* __restrict__ src, const uint8_t* 
 #undef RD8
 }
 
-// Persistent kernel, one warp per block at a time; blocks are handed out by a device counter.  Input and
-// output stay in global memory (more blocks in flight per SM than staging would allow); warps
-// 0..ENC_WARPS_PER_CTA-1 keep their hash table in shared memory, the ENC_GWARPS warps after them in
-// the `gtab` workspace (one 16 KiB slot per such warp of the grid).
-__global__ void __launch_bounds__(ENC_CTA_WARPS * 32, ENC_CTAS_PER_SM)
-encode_spec_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restrict__ srcOff,
-                   const int32_t* __restrict__ srcLen, uint8_t* __restrict__ dstBase,
-                   const int64_t* __restrict__ dstOff, const int32_t* __restrict__ dstCap,
-                   int32_t* __restrict__ outLen, int nBlocks, int level,
-                   uint32_t* __restrict__ nextBlock, uint8_t* __restrict__ gtab) {
-    extern __shared__ __align__(128) uint8_t smem_encs[];
-    const int wInCta = threadIdx.x >> 5;
+// Persistent encoder, one warp per block at a time, one warp per CTA (a CTA leaves as soon as ITS warp
+// runs out of blocks, so the CTAs of the next launch on another stream move in without a gap).  Blocks
+// are handed out by a device counter.  Input and output stay in global memory.  Two kernels pull from
+// the same counter and run concurrently: `encode_spec_kernel` keeps its 16 KiB hash table in shared
+// memory (ENC_SM_WARPS of them fill an SM), `encode_spec_gtab_kernel` keeps it in an L2-resident
+// workspace -- slower per block, but those warps use issue slots and registers the others leave idle.
+template <bool GTAB>
+__device__ __forceinline__ void encode_persistent_warp(
+        const uint8_t* __restrict__ srcBase, const int64_t* __restrict__ srcOff,
+        const int32_t* __restrict__ srcLen, uint8_t* __restrict__ dstBase,
+        const int64_t* __restrict__ dstOff, const int32_t* __restrict__ dstCap,
+        int32_t* __restrict__ outLen, const int nBlocks, int level,
+        uint32_t* __restrict__ nextBlock, uint16_t* const table, const int reserve) {
     const int lane = lane_id();
-    const bool inShared = wInCta < ENC_WARPS_PER_CTA;
-    uint16_t* const stable = reinterpret_cast<uint16_t*>(smem_encs + (inShared ? wInCta : 0) * ENC_SLOT_BYTES);
-    uint16_t* const gtable = reinterpret_cast<uint16_t*>(
-        gtab + ((size_t)blockIdx.x * ENC_GWARPS + (size_t)(inShared ? 0 : wInCta - ENC_WARPS_PER_CTA)) * ENC_SLOT_BYTES);
     const bool enforce32 = (level & ENC_FLAG_X32) != 0;   // LL.Enforce32 (LL.tools.cs:29): hash4 for the byU32 table
     level &= 0xFF;
     for (;;) {
         int b = 0;
         if (lane == 0) {
-            // the slower global-table warps leave the last blocks to the shared-memory warps (shorter tail)
-            if (!inShared && (int)*(volatile uint32_t*)nextBlock >= nBlocks - K4_ENC_TAIL * (int)gridDim.x * ENC_WARPS_PER_CTA) b = nBlocks;
+            // the slower global-table warps leave the last `reserve` blocks to the shared-memory warps
+            if (GTAB && (int)*(volatile uint32_t*)nextBlock >= nBlocks - reserve) b = nBlocks;
             else b = (int)atomicAdd(nextBlock, 1u);
         }
         b = __shfl_sync(FULL, b, 0);
@@ -259,12 +259,31 @@ encode_spec_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restric
         if (n_ <= 0) { if (lane == 0) outLen[b] = 0; continue; }
         if (level >= 3) { if (lane == 0) outLen[b] = -2; continue; }
         int r;
-        if (n_ >= LIMIT_64K) r = encode_block_warp(src, n_, dst, cap, 0x7fffffff, inShared ? (void*)stable : (void*)gtable, enforce32);
-        else if (inShared) r = encode_spec_warp<false, false>(src, nullptr, (uint32_t)n_, dst, cap, 0x7fffffff, stable);
-        else r = encode_spec_warp<false, false, true>(src, nullptr, (uint32_t)n_, dst, cap, 0x7fffffff, gtable);
+        if (n_ >= LIMIT_64K) r = encode_block_warp(src, n_, dst, cap, 0x7fffffff, table, enforce32);
+        else r = encode_spec_warp<false, false, GTAB>(src, nullptr, (uint32_t)n_, dst, cap, 0x7fffffff, table);
         if (lane == 0) outLen[b] = r <= 0 ? -1 : r;
         __syncwarp();
     }
+}
+
+__global__ void __launch_bounds__(32)
+encode_spec_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restrict__ srcOff,
+                   const int32_t* __restrict__ srcLen, uint8_t* __restrict__ dstBase,
+                   const int64_t* __restrict__ dstOff, const int32_t* __restrict__ dstCap,
+                   int32_t* __restrict__ outLen, int nBlocks, int level, uint32_t* __restrict__ nextBlock) {
+    extern __shared__ __align__(128) uint8_t smem_encs[];
+    encode_persistent_warp<false>(srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, nBlocks, level,
+                                  nextBlock, reinterpret_cast<uint16_t*>(smem_encs), 0);
+}
+
+__global__ void __launch_bounds__(32)
+encode_spec_gtab_kernel(const uint8_t* __restrict__ srcBase, const int64_t* __restrict__ srcOff,
+                        const int32_t* __restrict__ srcLen, uint8_t* __restrict__ dstBase,
+                        const int64_t* __restrict__ dstOff, const int32_t* __restrict__ dstCap,
+                        int32_t* __restrict__ outLen, int nBlocks, int level, uint32_t* __restrict__ nextBlock,
+                        uint8_t* __restrict__ gtab, int reserve) {
+    encode_persistent_warp<true>(srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, nBlocks, level, nextBlock,
+                                 reinterpret_cast<uint16_t*>(gtab + (size_t)blockIdx.x * ENC_SLOT_BYTES), reserve);
 }
 
 }  // namespace k4

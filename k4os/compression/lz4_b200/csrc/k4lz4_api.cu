@@ -78,37 +78,68 @@ void set_func_attrs(int dev) {
     std::call_once(g_attr_once[dev], [] {
         cudaFuncSetAttribute(k4::pickle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              k4::ENC_WARPS_PER_CTA * k4::ENC_SLOT_BYTES);
-        cudaFuncSetAttribute(k4::encode_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             k4::ENC_WARPS_PER_CTA * k4::ENC_SLOT_BYTES);
+        // both encoder kernels ask for the same shared-memory / L1 split (they share SMs): just enough for the
+        // shared-memory tables (+1 KiB the hardware reserves per CTA), the rest stays L1 for the input windows
+        const int carve = (k4::ENC_SM_WARPS * (k4::ENC_SLOT_BYTES + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024);
+        cudaFuncSetAttribute(k4::encode_spec_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve > 100 ? 100 : carve);
+        cudaFuncSetAttribute(k4::encode_spec_gtab_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve > 100 ? 100 : carve);
     });
 }
 
-// Enqueues the persistent block encoder: one grid-filling launch; its workspace (block counter + the
-// global-memory hash tables of the ENC_GWARPS warps per CTA) comes from the private stream-ordered pool.
+// Enqueues the block encoder: a shared-memory-table kernel on `st` and, when the batch is big enough for
+// it to pay, a global-memory-table kernel on a helper stream that runs beside it (fork / join by events).
+// Both are persistent and pull blocks from one device counter.  The workspace (counter + the global
+// tables) comes from the private stream-ordered pool.  `forceG`: the caller overlaps this launch with the
+// next one (host pipeline), so slow last blocks do not idle the GPU.
 cudaError_t encode_launch(const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen,
                           uint8_t* dstBase, const int64_t* dstOff, const int32_t* dstCap,
-                          int32_t* outLen, int n, int level, cudaStream_t st) {
+                          int32_t* outLen, int n, int level, cudaStream_t st, bool forceG, int* launches) {
     int dev = 0;
     cudaGetDevice(&dev);
     k4::DecodeDev* D = k4::decode_dev(dev);
     if (!D || D->err != cudaSuccess) return D ? D->err : cudaErrorInvalidDevice;
-    const int want = (n + k4::ENC_CTA_WARPS - 1) / k4::ENC_CTA_WARPS;
-    const int full = D->sms * k4::ENC_CTAS_PER_SM;
-    const int ctas = want < full ? want : full;
-    const size_t tabBytes = (size_t)ctas * k4::ENC_GWARPS * k4::ENC_SLOT_BYTES;
+    const int wave = D->sms * k4::ENC_SM_WARPS;
+    const int gridS = n < wave ? n : wave;
+    // The global-table warps need longer per block than the shared-memory warps: a batch that the latter
+    // finish in one round goes to them alone.
+    (void)forceG;
+    const bool useG = k4::ENC_GM_WARPS > 0 && n > wave;
+    const int gridG = useG ? D->sms * k4::ENC_GM_WARPS : 0;
+    const size_t tabBytes = (size_t)gridG * k4::ENC_SLOT_BYTES;
     uint8_t* ws = nullptr;
     cudaError_t e = cudaMallocFromPoolAsync((void**)&ws, 256 + tabBytes, D->pool, st);
     if (e != cudaSuccess) return e;
+    uint32_t* counter = reinterpret_cast<uint32_t*>(ws);
     e = cudaMemsetAsync(ws, 0, 4, st);
-    if (e == cudaSuccess) {
-        k4::encode_spec_kernel<<<ctas, k4::ENC_CTA_WARPS * 32, k4::ENC_WARPS_PER_CTA * k4::ENC_SLOT_BYTES, st>>>(
-            srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, n, level,
-            reinterpret_cast<uint32_t*>(ws), ws + 256);
-        e = cudaGetLastError();
+    cudaEvent_t fork = nullptr, join = nullptr;
+    if (e == cudaSuccess && useG) {
+        cudaStream_t hs = D->helper[D->nextHelper.fetch_add(1) % 4];
+        e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(fork, st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(hs, fork, 0);
+        if (e == cudaSuccess) {
+            k4::encode_spec_gtab_kernel<<<gridG, 32, 0, hs>>>(srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen,
+                                                             n, level, counter, ws + 256, wave);
+            e = cudaGetLastError();
+            if (launches) (*launches)++;
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(join, hs);
     }
+    if (e == cudaSuccess && gridS > 0) {
+        k4::encode_spec_kernel<<<gridS, 32, k4::ENC_SLOT_BYTES, st>>>(srcBase, srcOff, srcLen, dstBase, dstOff, dstCap,
+                                                                      outLen, n, level, counter);
+        e = cudaGetLastError();
+        if (launches) (*launches)++;
+    }
+    if (join && e == cudaSuccess) e = cudaStreamWaitEvent(st, join, 0);
+    if (fork) cudaEventDestroy(fork);
+    if (join) cudaEventDestroy(join);
     cudaFreeAsync(ws, st);
     return e;
 }
+
+constexpr int ENC_HINT_OVERLAPPED = 0x10000;   // internal `level` bit (host pipeline -> launch_op): see encode_launch
 
 struct DevArgs {
     const uint8_t* srcBase; const int64_t* srcOff; const int32_t* srcLen;
@@ -123,10 +154,12 @@ cudaError_t launch_op(Op op, const DevArgs& a, cudaStream_t st) {
     set_func_attrs(dev);
     switch (op) {
     case OP_ENCODE: {
+        int nl = 0;
         const cudaError_t ee = encode_launch(a.srcBase, a.srcOff, a.srcLen, a.dstBase, a.dstOff, a.dstCap,
-                                             a.outLen, a.n, a.level, st);
+                                             a.outLen, a.n, a.level & ~ENC_HINT_OVERLAPPED, st,
+                                             (a.level & ENC_HINT_OVERLAPPED) != 0, &nl);
+        g_launches += nl;
         if (ee != cudaSuccess) { (void)cudaGetLastError(); return ee; }
-        g_launches++;
         break;
     }
     case OP_DECODE: {
@@ -236,10 +269,12 @@ struct Slot {          // one in-flight chunk
     int state = 0;                    // 0 idle, 1 kernel + outLen enqueued, 2 data D2H enqueued
 };
 
+constexpr int NSLOT = 4;   // chunks in flight per device (see run_host_slice)
+
 struct DevCtx {
     int dev = -1;
     std::mutex mu;
-    Slot slot[3];
+    Slot slot[NSLOT];
     bool init = false;
 };
 
@@ -421,7 +456,7 @@ int enqueue_chunk(Op op, const HostArgs& a, Slot& s, int64_t b0, int64_t b1) {
                                (size_t)srcBytes, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(s.dMeta.p, s.hMeta.p, (size_t)nb * 24, cudaMemcpyHostToDevice, st));
     DevArgs d{(const uint8_t*)s.dSrc.p, dSrcOff, dSrcLen, (uint8_t*)s.dDst.p, dDstOff, dDstCap,
-              dOutLen, (int)nb, a.level};
+              dOutLen, (int)nb, a.level | (op == OP_ENCODE ? ENC_HINT_OVERLAPPED : 0)};
     CU_TRY(launch_op(op, d, st));
     // outLen lands at the front of hMeta (offset arrays there are no longer needed once the
     // H2D above has been issued *and completed*; stream order guarantees that)
@@ -432,12 +467,12 @@ int enqueue_chunk(Op op, const HostArgs& a, Slot& s, int64_t b0, int64_t b1) {
     return K4LZ4_OK;
 }
 
-// blocks the encoder processes at once on `dev`: SMs x CTAs per SM x warps per CTA
+// blocks the encoder finishes in about one shared-memory-warp block time on `dev` (a global-table warp counts half)
 int64_t enc_wave_blocks(int dev) {
     static int sms[64] = {0};
     if (dev < 0 || dev >= 64) return 1;
     if (!sms[dev]) { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) v = 0; sms[dev] = v > 0 ? v : -1; }
-    return sms[dev] > 0 ? (int64_t)sms[dev] * k4::ENC_CTAS_PER_SM * k4::ENC_CTA_WARPS : 1;
+    return sms[dev] > 0 ? (int64_t)sms[dev] * (k4::ENC_SM_WARPS + (k4::ENC_GM_WARPS + 1) / 2) : 1;
 }
 
 // One device, blocks [b0, b1): chunked + double-buffered (H2D/kernel/D2H of chunk c overlap
@@ -455,35 +490,43 @@ int run_host_slice(Op op, const HostArgs& a, int64_t b0, int64_t b1, int dev) {
     int rc = K4LZ4_OK;
     int64_t i = b0;
     int c = 0;
-    // three chunks in flight: stage 1 (H2D + kernel + results) of chunk c overlaps stage 2 (data
-    // D2H) of chunk c-1 and stage 3 (host scatter, if needed) of chunk c-2
+    // Four chunks in flight.  While the host waits for the kernel of chunk c-2 (stage 2: per-block results,
+    // gather of the produced bytes, data D2H) and scatters chunk c-3 (stage 3), the kernel of chunk c-1 runs
+    // and chunk c is already queued behind it with its H2D under way -- the GPU never waits for PCIe or for
+    // the host.
     while (i < b1) {
         int64_t bytes = 0, j = i;
-        // The encoder keeps one warp busy per block for milliseconds (a serial chain per block): a chunk
-        // should fill the GPU's warp slots a whole number of times, else its kernel ends on a half-empty
-        // wave.  Encode / pickle chunks therefore hold a multiple of `wave` blocks (up to 768 MiB).
-        const bool encLike = op == OP_ENCODE || op == OP_PICKLE || op == OP_PICKLEW;
-        const int64_t limit = encLike ? 4 * CHUNK_BYTES : CHUNK_BYTES;
-        const int64_t wave = encLike ? enc_wave_blocks(dev) : 1;
-        int64_t jWave = -1;
-        while (j < b1 && (j == i || bytes + src_size(a, j) + dst_room(op, a, j) <= limit)) {
+        // Encode: a warp works on one block for milliseconds.  Consecutive chunks' kernels overlap (one-warp
+        // CTAs leave individually and the next launch, on another stream, moves in), so chunk size only has
+        // to cover the latency of a chunk's slowest (global-table) blocks: 4 waves in the middle of a
+        // batch; one and two waves at both ends, so that the pipeline fills and drains fast.
+        int64_t limit = CHUNK_BYTES, maxBlocks = INT64_MAX;
+        if (op == OP_ENCODE) {
+            const int64_t W = enc_wave_blocks(dev), rem = b1 - i;
+            limit = 1536ll << 20;
+            if (c == 0) maxBlocks = W;
+            else if (c == 1) maxBlocks = 2 * W;
+            else if (2 * rem <= 3 * W) maxBlocks = rem;
+            else if (2 * rem <= 7 * W) maxBlocks = std::min<int64_t>(2 * W, rem - W);
+            else maxBlocks = std::max<int64_t>(std::min<int64_t>(4 * W, rem - 3 * W), W);
+        } else if (op == OP_PICKLE || op == OP_PICKLEW) {
+            limit = 4 * CHUNK_BYTES;
+        }
+        while (j < b1 && j - i < maxBlocks && (j == i || bytes + src_size(a, j) + dst_room(op, a, j) <= limit)) {
             bytes += src_size(a, j) + dst_room(op, a, j);
             j++;
-            if (wave > 1 && (j - i) % wave == 0) jWave = j;
         }
-        if (jWave > i && j < b1) j = jWave;                    // not the last chunk: cut at a wave boundary
-        Slot& s = ctx->slot[c % 3];
-        if ((rc = stage3_slot(op, a, s)) != K4LZ4_OK) break;
+        Slot& s = ctx->slot[c % NSLOT];
+        if ((rc = stage3_slot(op, a, s)) != K4LZ4_OK) break;                       // chunk c-4: long done
         if ((rc = enqueue_chunk(op, a, s, i, j)) != K4LZ4_OK) break;
-        if (c >= 1 && (rc = stage2_slot(op, a, ctx->slot[(c - 1) % 3])) != K4LZ4_OK) break;
-        if (c >= 2 && (rc = stage3_slot(op, a, ctx->slot[(c - 2) % 3])) != K4LZ4_OK) break;
+        if (c >= 2 && (rc = stage2_slot(op, a, ctx->slot[(c - 2) % NSLOT])) != K4LZ4_OK) break;
+        if (c >= 3 && (rc = stage3_slot(op, a, ctx->slot[(c - 3) % NSLOT])) != K4LZ4_OK) break;
         i = j; c++;
     }
     if (rc != K4LZ4_OK) { for (auto& s : ctx->slot) s.state = 0; cudaDeviceSynchronize(); return rc; }
-    for (int k = 0; k < 3; k++) {                          // drain in issue order
-        const int idx = ((c - 3 + k) % 3 + 3) % 3;
-        if ((rc = stage3_slot(op, a, ctx->slot[idx])) != K4LZ4_OK) break;
-    }
+    // drain in issue order: results + data D2H of everything still on the device first, then the scatters
+    for (int k = c - NSLOT; k < c && rc == K4LZ4_OK; k++) if (k >= 0) rc = stage2_slot(op, a, ctx->slot[k % NSLOT]);
+    for (int k = c - NSLOT; k < c && rc == K4LZ4_OK; k++) if (k >= 0) rc = stage3_slot(op, a, ctx->slot[k % NSLOT]);
     if (rc != K4LZ4_OK) { for (auto& s : ctx->slot) s.state = 0; cudaDeviceSynchronize(); }
     return rc;
 }
@@ -584,6 +627,7 @@ int run_host(Op op, const HostArgs& a, int64_t n, int device) {
 int run(Op op, const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen, uint8_t* dstBase,
         const int64_t* dstOff, const int32_t* dstCap, int32_t* outLen, int64_t n, int level,
         int memKind, void* stream, int device) {
+    level &= 0xFF | k4::ENC_FLAG_X32;                      // internal hint bits never come from outside
     if (memKind == K4LZ4_MEM_DEVICE) {
         if (n > INT32_MAX) return fail(K4LZ4_E_ARG, "too many blocks");
         DevArgs d{srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, (int)n, level};
