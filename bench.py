@@ -389,6 +389,8 @@ def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
     from k4os.compression.lz4_b200 import _native as N, batch as B
+    if args.lib:
+        N.SO_PATH = os.path.abspath(args.lib)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -566,6 +568,8 @@ def run_ours(args) -> None:
 
     # ---- aux: pickler (configs[3]) device-resident throughput ----
     try:
+        if args.no_aux:
+            raise RuntimeError("skipped (--no-aux)")
         pn = 1 << 20
         prng = np.random.default_rng(42)
         psz = np.where(prng.random(pn) < 0.5, prng.choice([256, 512, 1024, 2048, 4096], pn),
@@ -685,6 +689,8 @@ def main():
     ap.add_argument("--no-all-devices", dest="all_devices", action="store_false",
                     help="skip aux.all_devices_one_call (ONE host-memory call per direction over every visible GPU; "
                          "runs on rank 0 whenever more than one GPU is visible)")
+    ap.add_argument("--lib", default=None, help="development only: another build of libk4lz4.so (A/B runs of kernel variants)")
+    ap.add_argument("--no-aux", action="store_true", help="development only: skip the aux legs (pickler, all-devices call)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -35,7 +35,6 @@
 // Reference semantics: /root/reference/src/K4os.Compression.LZ4/Engine/x64/LL64.dec.cs:124-477,
 // Engine/LL.tools.cs:165-193 (LZ4_readVLE), LZ4Codec.cs:104-115.
 #pragma once
-#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
@@ -699,8 +698,7 @@ struct DecodeDev {
     cudaMemPool_t pool = nullptr;
     int sms = 0;
     cudaError_t err = cudaSuccess;
-    cudaStream_t helper[4] = {nullptr, nullptr, nullptr, nullptr};   // side streams of the encoder (encode_launch)
-    std::atomic<unsigned> nextHelper{0};
+    cudaStream_t helper = nullptr;   // side stream of the encoder (encode_launch)
 };
 
 inline DecodeDev* decode_dev(int dev) {
@@ -727,7 +725,7 @@ inline DecodeDev* decode_dev(int dev) {
                 cudaMemPoolSetAttribute(d->pool, cudaMemPoolAttrReleaseThreshold, &keep);
             }
         }
-        for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&d->helper[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->helper, cudaStreamNonBlocking);
         d->err = e;
     });
     return d;

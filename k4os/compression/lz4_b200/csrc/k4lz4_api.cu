@@ -89,11 +89,10 @@ void set_func_attrs(int dev) {
 // Enqueues the block encoder: a shared-memory-table kernel on `st` and, when the batch is big enough for
 // it to pay, a global-memory-table kernel on a helper stream that runs beside it (fork / join by events).
 // Both are persistent and pull blocks from one device counter.  The workspace (counter + the global
-// tables) comes from the private stream-ordered pool.  `forceG`: the caller overlaps this launch with the
-// next one (host pipeline), so slow last blocks do not idle the GPU.
+// tables) comes from the private stream-ordered pool.
 cudaError_t encode_launch(const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen,
                           uint8_t* dstBase, const int64_t* dstOff, const int32_t* dstCap,
-                          int32_t* outLen, int n, int level, cudaStream_t st, bool forceG, int* launches) {
+                          int32_t* outLen, int n, int level, cudaStream_t st, int* launches) {
     int dev = 0;
     cudaGetDevice(&dev);
     k4::DecodeDev* D = k4::decode_dev(dev);
@@ -102,7 +101,6 @@ cudaError_t encode_launch(const uint8_t* srcBase, const int64_t* srcOff, const i
     const int gridS = n < wave ? n : wave;
     // The global-table warps need longer per block than the shared-memory warps: a batch that the latter
     // finish in one round goes to them alone.
-    (void)forceG;
     const bool useG = k4::ENC_GM_WARPS > 0 && n > wave;
     const int gridG = useG ? D->sms * k4::ENC_GM_WARPS : 0;
     const size_t tabBytes = (size_t)gridG * k4::ENC_SLOT_BYTES;
@@ -113,7 +111,10 @@ cudaError_t encode_launch(const uint8_t* srcBase, const int64_t* srcOff, const i
     e = cudaMemsetAsync(ws, 0, 4, st);
     cudaEvent_t fork = nullptr, join = nullptr;
     if (e == cudaSuccess && useG) {
-        cudaStream_t hs = D->helper[D->nextHelper.fetch_add(1) % 4];
+        // ONE side stream per device: the global-table kernels of consecutive chunks run one after the other, so an
+        // SM never holds more than ENC_GM_WARPS of them (CTAs of a queued launch would otherwise fill the SM's spare
+        // CTA slots and crowd out the mix; measured slower)
+        cudaStream_t hs = D->helper;
         e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventRecord(fork, st);
@@ -139,8 +140,6 @@ cudaError_t encode_launch(const uint8_t* srcBase, const int64_t* srcOff, const i
     return e;
 }
 
-constexpr int ENC_HINT_OVERLAPPED = 0x10000;   // internal `level` bit (host pipeline -> launch_op): see encode_launch
-
 struct DevArgs {
     const uint8_t* srcBase; const int64_t* srcOff; const int32_t* srcLen;
     uint8_t* dstBase; const int64_t* dstOff; const int32_t* dstCap;
@@ -156,8 +155,7 @@ cudaError_t launch_op(Op op, const DevArgs& a, cudaStream_t st) {
     case OP_ENCODE: {
         int nl = 0;
         const cudaError_t ee = encode_launch(a.srcBase, a.srcOff, a.srcLen, a.dstBase, a.dstOff, a.dstCap,
-                                             a.outLen, a.n, a.level & ~ENC_HINT_OVERLAPPED, st,
-                                             (a.level & ENC_HINT_OVERLAPPED) != 0, &nl);
+                                             a.outLen, a.n, a.level, st, &nl);
         g_launches += nl;
         if (ee != cudaSuccess) { (void)cudaGetLastError(); return ee; }
         break;
@@ -266,10 +264,12 @@ struct Slot {          // one in-flight chunk
     std::vector<int64_t> packedDstOff;
     int64_t dstBytes = 0;             // device-side extent of the destination region of the chunk
     bool direct = false;              // stage 2 copied straight into the caller's buffer
-    int state = 0;                    // 0 idle, 1 kernel + outLen enqueued, 2 data D2H enqueued
+    int state = 0;                    // 0 idle, 3 inputs on their way, 1 kernel + outLen enqueued, 2 data D2H enqueued
+    DevArgs launch{};                 // the chunk's kernel arguments (state 3 -> 1)
 };
 
-constexpr int NSLOT = 4;   // chunks in flight per device (see run_host_slice)
+constexpr int ENC_BIG_WAVES = 6;        // encode chunks in the middle of a batch: this many waves of blocks
+constexpr int NSLOT = 4;                // chunks in flight per device (see run_host_slice)
 
 struct DevCtx {
     int dev = -1;
@@ -309,6 +309,7 @@ inline int64_t dst_room(Op op, const HostArgs& a, int64_t i) {
 inline int64_t src_size(const HostArgs& a, int64_t i) { return a.srcLen[i] < 0 ? 0 : a.srcLen[i]; }
 
 void parallel_for_blocks(int64_t b0, int64_t b1, int64_t bytesHint, const std::function<void(int64_t, int64_t)>& fn);
+int launch_chunk(Op op, Slot& s);
 
 constexpr int64_t CHUNK_BYTES = 192ll << 20;   // src + dst payload per in-flight chunk
 
@@ -335,6 +336,7 @@ void scatter_chunk(Op op, const HostArgs& a, Slot& s) {
 // case) the bytes go straight into the caller's buffer in one copy; otherwise through the pinned
 // staging buffer and a host-side scatter (stage 3) that leaves bytes >= outLen[i] untouched.
 int stage2_slot(Op op, const HostArgs& a, Slot& s) {
+    if (s.state == 3) { int rc = launch_chunk(op, s); if (rc != K4LZ4_OK) return rc; }
     if (s.state != 1) return K4LZ4_OK;
     CU_TRY(cudaStreamSynchronize(s.stream));
     memcpy(a.outLen + s.b0, (const int32_t*)s.hMeta.p, sizeof(int32_t) * (size_t)(s.b1 - s.b0));
@@ -385,7 +387,7 @@ int stage2_slot(Op op, const HostArgs& a, Slot& s) {
 
 // stage 3: data has landed
 int stage3_slot(Op op, const HostArgs& a, Slot& s) {
-    if (s.state == 1) { int rc = stage2_slot(op, a, s); if (rc != K4LZ4_OK) return rc; }
+    if (s.state == 1 || s.state == 3) { int rc = stage2_slot(op, a, s); if (rc != K4LZ4_OK) return rc; }
     if (s.state != 2) return K4LZ4_OK;
     s.state = 0;
     CU_TRY(cudaStreamSynchronize(s.stream));
@@ -393,6 +395,7 @@ int stage3_slot(Op op, const HostArgs& a, Slot& s) {
     return K4LZ4_OK;
 }
 
+// stage 1a: stage the chunk's inputs and block table on the device (asynchronous copies on the slot's stream)
 int enqueue_chunk(Op op, const HostArgs& a, Slot& s, int64_t b0, int64_t b1) {
     const int64_t nb = b1 - b0;
     s.b0 = b0; s.b1 = b1;
@@ -455,14 +458,21 @@ int enqueue_chunk(Op op, const HostArgs& a, Slot& s, int64_t b0, int64_t b1) {
         CU_TRY(cudaMemcpyAsync(s.dSrc.p, srcPacked ? (const void*)s.hSrc.p : (const void*)(a.srcBase + sLo),
                                (size_t)srcBytes, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(s.dMeta.p, s.hMeta.p, (size_t)nb * 24, cudaMemcpyHostToDevice, st));
-    DevArgs d{(const uint8_t*)s.dSrc.p, dSrcOff, dSrcLen, (uint8_t*)s.dDst.p, dDstOff, dDstCap,
-              dOutLen, (int)nb, a.level | (op == OP_ENCODE ? ENC_HINT_OVERLAPPED : 0)};
-    CU_TRY(launch_op(op, d, st));
-    // outLen lands at the front of hMeta (offset arrays there are no longer needed once the
-    // H2D above has been issued *and completed*; stream order guarantees that)
-    CU_TRY(cudaMemcpyAsync(s.hMeta.p, dOutLen, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+    s.launch = DevArgs{(const uint8_t*)s.dSrc.p, dSrcOff, dSrcLen, (uint8_t*)s.dDst.p, dDstOff, dDstCap,
+                       dOutLen, (int)nb, a.level};
     s.dDstOffArr = dDstOff;
     s.dOutLenArr = dOutLen;
+    s.state = 3;
+    return K4LZ4_OK;
+}
+
+// stage 1b: the kernel of a chunk whose inputs are on their way (same stream), then its per-block results
+int launch_chunk(Op op, Slot& s) {
+    if (s.state != 3) return K4LZ4_OK;
+    CU_TRY(launch_op(op, s.launch, s.stream));
+    // outLen lands at the front of hMeta (offset arrays there are no longer needed once the
+    // H2D of the chunk has been issued *and completed*; stream order guarantees that)
+    CU_TRY(cudaMemcpyAsync(s.hMeta.p, s.launch.outLen, (size_t)s.launch.n * 4, cudaMemcpyDeviceToHost, s.stream));
     s.state = 1;
     return K4LZ4_OK;
 }
@@ -488,27 +498,22 @@ int run_host_slice(Op op, const HostArgs& a, int64_t b0, int64_t b1, int dev) {
         ctx->init = true;
     }
     int rc = K4LZ4_OK;
-    int64_t i = b0;
-    int c = 0;
-    // Four chunks in flight.  While the host waits for the kernel of chunk c-2 (stage 2: per-block results,
-    // gather of the produced bytes, data D2H) and scatters chunk c-3 (stage 3), the kernel of chunk c-1 runs
-    // and chunk c is already queued behind it with its H2D under way -- the GPU never waits for PCIe or for
-    // the host.
-    while (i < b1) {
+    // Chunk boundaries.  Encode: a warp works on one block for milliseconds; consecutive chunks' kernels
+    // overlap (one-warp CTAs leave individually and the next launch, on another stream, moves in), so a
+    // chunk only has to be long enough to hide its copies and the host's work behind the previous kernel:
+    // ENC_BIG_WAVES waves in the middle of a batch, one and two waves at both ends so that the pipeline
+    // fills and drains fast.
+    auto chunk_end = [&](int64_t i, int c) {
         int64_t bytes = 0, j = i;
-        // Encode: a warp works on one block for milliseconds.  Consecutive chunks' kernels overlap (one-warp
-        // CTAs leave individually and the next launch, on another stream, moves in), so chunk size only has
-        // to cover the latency of a chunk's slowest (global-table) blocks: 4 waves in the middle of a
-        // batch; one and two waves at both ends, so that the pipeline fills and drains fast.
         int64_t limit = CHUNK_BYTES, maxBlocks = INT64_MAX;
         if (op == OP_ENCODE) {
             const int64_t W = enc_wave_blocks(dev), rem = b1 - i;
-            limit = 1536ll << 20;
+            limit = 2560ll << 20;
             if (c == 0) maxBlocks = W;
             else if (c == 1) maxBlocks = 2 * W;
             else if (2 * rem <= 3 * W) maxBlocks = rem;
             else if (2 * rem <= 7 * W) maxBlocks = std::min<int64_t>(2 * W, rem - W);
-            else maxBlocks = std::max<int64_t>(std::min<int64_t>(4 * W, rem - 3 * W), W);
+            else maxBlocks = std::max<int64_t>(std::min<int64_t>(ENC_BIG_WAVES * W, rem - 3 * W), W);
         } else if (op == OP_PICKLE || op == OP_PICKLEW) {
             limit = 4 * CHUNK_BYTES;
         }
@@ -516,17 +521,39 @@ int run_host_slice(Op op, const HostArgs& a, int64_t b0, int64_t b1, int dev) {
             bytes += src_size(a, j) + dst_room(op, a, j);
             j++;
         }
-        Slot& s = ctx->slot[c % NSLOT];
-        if ((rc = stage3_slot(op, a, s)) != K4LZ4_OK) break;                       // chunk c-4: long done
-        if ((rc = enqueue_chunk(op, a, s, i, j)) != K4LZ4_OK) break;
-        if (c >= 2 && (rc = stage2_slot(op, a, ctx->slot[(c - 2) % NSLOT])) != K4LZ4_OK) break;
-        if (c >= 3 && (rc = stage3_slot(op, a, ctx->slot[(c - 3) % NSLOT])) != K4LZ4_OK) break;
-        i = j; c++;
+        return j;
+    };
+    // Four chunks in flight, copies issued two chunks ahead, kernels one:
+    //   inputs(c+1) -> wait kernel(c-1), its results, gather + data D2H (stage 2) -> kernel(c+1) -> scatter(c-2)
+    // so while kernel c runs, chunk c+1 is queued behind it with its inputs already on the device, the data
+    // of chunk c-1 crosses PCIe and the host scatters chunk c-2: the GPU never waits for PCIe or for the host.
+    // No more than two kernels are queued at any time (a third one would crowd the SMs with the CTAs of
+    // three launches; measured slower).
+    auto slot_of = [&](int c) -> Slot& { return ctx->slot[((c % NSLOT) + NSLOT) % NSLOT]; };
+    int64_t next = b0;                                     // first block not yet staged
+    int staged = 0;                                        // chunks whose inputs have been issued
+    auto stage_next = [&]() -> int {
+        if (next >= b1) return K4LZ4_OK;
+        Slot& s = slot_of(staged);
+        int r = stage3_slot(op, a, s);                     // chunk staged-4: long done
+        if (r != K4LZ4_OK) return r;
+        const int64_t j = chunk_end(next, staged);
+        r = enqueue_chunk(op, a, s, next, j);
+        next = j; staged++;
+        return r;
+    };
+    rc = stage_next();
+    if (rc == K4LZ4_OK) rc = launch_chunk(op, slot_of(0));
+    for (int c = 0; rc == K4LZ4_OK && c < staged; c++) {
+        if ((rc = stage_next()) != K4LZ4_OK) break;                                       // inputs of chunk c+1
+        if (c >= 1 && (rc = stage2_slot(op, a, slot_of(c - 1))) != K4LZ4_OK) break;       // kernel c-1 done
+        if (c + 1 < staged && (rc = launch_chunk(op, slot_of(c + 1))) != K4LZ4_OK) break; // kernel c+1 queued
+        if (c >= 2 && (rc = stage3_slot(op, a, slot_of(c - 2))) != K4LZ4_OK) break;       // scatter c-2
     }
     if (rc != K4LZ4_OK) { for (auto& s : ctx->slot) s.state = 0; cudaDeviceSynchronize(); return rc; }
     // drain in issue order: results + data D2H of everything still on the device first, then the scatters
-    for (int k = c - NSLOT; k < c && rc == K4LZ4_OK; k++) if (k >= 0) rc = stage2_slot(op, a, ctx->slot[k % NSLOT]);
-    for (int k = c - NSLOT; k < c && rc == K4LZ4_OK; k++) if (k >= 0) rc = stage3_slot(op, a, ctx->slot[k % NSLOT]);
+    for (int k = staged - NSLOT; k < staged && rc == K4LZ4_OK; k++) if (k >= 0) rc = stage2_slot(op, a, slot_of(k));
+    for (int k = staged - NSLOT; k < staged && rc == K4LZ4_OK; k++) if (k >= 0) rc = stage3_slot(op, a, slot_of(k));
     if (rc != K4LZ4_OK) { for (auto& s : ctx->slot) s.state = 0; cudaDeviceSynchronize(); }
     return rc;
 }
@@ -627,7 +654,6 @@ int run_host(Op op, const HostArgs& a, int64_t n, int device) {
 int run(Op op, const uint8_t* srcBase, const int64_t* srcOff, const int32_t* srcLen, uint8_t* dstBase,
         const int64_t* dstOff, const int32_t* dstCap, int32_t* outLen, int64_t n, int level,
         int memKind, void* stream, int device) {
-    level &= 0xFF | k4::ENC_FLAG_X32;                      // internal hint bits never come from outside
     if (memKind == K4LZ4_MEM_DEVICE) {
         if (n > INT32_MAX) return fail(K4LZ4_E_ARG, "too many blocks");
         DevArgs d{srcBase, srcOff, srcLen, dstBase, dstOff, dstCap, outLen, (int)n, level};

@@ -326,6 +326,34 @@ def test_datagen_blocks_encode_and_decode_gpu(k4, chk):
         assert st["tile"] + st["tile_big"] == nb and st["generic"] == 0, st   # clean data never needs the exact fallback
 
 
+def test_encode_many_blocks_through_both_kernels_and_chunks(k4, chk):
+    """More blocks than the shared-memory-table kernel takes in one round: the global-table kernel runs
+    beside it and the host path cuts the batch into several chunks (graded sizes).  Every block, whichever
+    warp kind encoded it, must be the reference's bytes -- including a few blocks of >= 65 547 bytes (u32
+    table in the global workspace), empty blocks and limited-output failures."""
+    import oracle
+    port = oracle.Port()
+    rng = np.random.default_rng(77)
+    n = 9000
+    raw = port.datagen(40 << 20, 0.55, 0.0, 99)
+    sizes = rng.integers(0, 8192, n)
+    sizes[rng.integers(0, n, 40)] = 0
+    for k, big in zip(rng.integers(0, n, 6), (65546, 65547, 70000, 131072, 65600, 90000)):
+        sizes[k] = big
+    off = np.concatenate([[0], np.cumsum(sizes)[:-1]]) % ((40 << 20) - 140000)
+    blocks = [raw[o:o + z].tobytes() for o, z in zip(off, sizes)]
+    caps = [k4.LZ4Codec.MaximumOutputSize(len(b)) for b in blocks]
+    tight = rng.integers(0, n, 200)
+    for k in tight:
+        caps[k] = max(0, len(blocks[k]) // 3)                       # forces limitedOutput paths, mostly failures
+    enc, lens = k4.batch.encode_batch_host(blocks, caps)
+    for i, b in enumerate(blocks):
+        r, c = chk.encode(b, caps[i])
+        assert int(lens[i]) == (r if r > 0 else (0 if len(b) == 0 else -1)), (i, len(b), caps[i], int(lens[i]), r)
+        if r > 0:
+            assert enc[i] == c, (i, len(b))
+
+
 def test_issue64_block0_reencoded_by_gpu(k4, chk):
     expect = open(os.path.join(G, "issue64_block0.bin"), "rb").read()
     enc, lens = k4.batch.encode_batch_host([expect])

@@ -49,7 +49,6 @@ dec = [d for d in ks if d['Kernel Name'][0].startswith('decode_tile_kernel')][0]
 big = [d for d in ks if d['Kernel Name'][0].startswith('decode_tile_big')]
 rest = [d for d in ks if d['Kernel Name'][0].startswith('decode_rest')]
 encs = [d for d in ks if d['Kernel Name'][0].startswith('encode_spec')]
-enc8k = raw(enc_rep)[0]
 dr, dw = num(dec, 'dram__bytes_read.sum'), num(dec, 'dram__bytes_write.sum')
 inst = float(dec['smsp__inst_executed.sum'][0].replace(',', ''))
 nblk = int(dec['Grid Size'][0].strip('()').split(',')[0])
@@ -77,29 +76,35 @@ open(f'profiles/ncu_{tag}_decode_summary.txt', 'w').write(f"""# ncu --set full -
    SASS aggregated through nvdisasm -g line info by tools/ncu_lines.py; line numbers are those of the committed decode_tile.cuh)
 {lines(step_rep, 'decode_tile_kernelE', '^decode_tile_kernel', 45)}
 """)
-e = encs[0] if encs else None
-open(f'profiles/ncu_{tag}_encode_summary.txt', 'w').write(f"""# (a) the encode pass of the bench step (65 536 blocks of the configs[2] workload), same ncu command as ncu_{tag}_decode_summary.txt
-{fmt(e) if e else '  (not captured)'}
+enc_rows = raw(enc_rep)
+enc_total = lambda rows: sum(num(d, 'dram__bytes_read.sum') + num(d, 'dram__bytes_write.sum') for d in rows)
+open(f'profiles/ncu_{tag}_encode_summary.txt', 'w').write(f"""# The encoder is two persistent kernels that pull blocks from one device counter and normally run SIDE BY SIDE
+# (encode_spec_gtab_kernel: hash tables in an L2-resident workspace, 25 one-warp CTAs per SM; encode_spec_kernel: hash tables
+# in shared memory, 7 one-warp CTAs per SM).  ncu serialises kernels, so under the profiler the kernel that is launched first
+# (gtab) encodes every block but the last wave and the other one gets the rest: the per-kernel counters below are valid per
+# kernel, the split of the work between them is not what an unprofiled run does.
 
-# (b) ncu --set full --import-source on --clock-control none -k regex:encode_spec_kernel -c 1
+# (a) the encode pass of the bench step (65 536 blocks of the configs[2] workload), same ncu command as ncu_{tag}_decode_summary.txt
+{chr(10).join(fmt(e) + chr(10) for e in encs) if encs else '  (not captured)'}
+
+# (b) ncu --set full --import-source on --clock-control none -k regex:encode_spec -c 2
 #   python tools/dbench.py --blocks 8192 --data datagen --mp 550 --reps 1 --what encode     (1/8 of the pass; source counters)
-{fmt(enc8k)}
+{chr(10).join(fmt(e) + chr(10) for e in enc_rows)}
 
-   One warp per block, 14 blocks in flight per SM (two CTAs of 7 warps x 16 KiB hash table).  The chain per sequence is
-   serial (the reference's single-slot table history); ~11 cycles per dependent instruction, ~290 warp instructions per
-   sequence.  Global loads are dominated by the 32 speculative candidate reads per probe batch (L1 hit ~50 %, L2 hit > 90 %).
-   An 8-bit tag filter in front of the candidate reads (-DK4_ENC_TAGS=1: 24 KiB per warp, 9 blocks per SM) removes most
-   of them but measured SLOWER (17.8 vs 23.8 GB/s on this workload): occupancy, not load bandwidth, is what the chains need.
+   One warp per block; ~290 warp instructions per sequence on a serial chain of dependent memory round trips (position ->
+   slot -> candidate bytes -> count), so throughput = blocks in flight / latency: 32 one-warp CTAs per SM (the CTA limit, 64
+   registers each).  Only 7 of them keep their table in shared memory -- the rest of the 256 KiB stays L1, which the input
+   windows need more than the tables need shared memory (sweep in DESIGN.md 4.2).
 
-== per-source-line hot spots of (b)
-{lines(enc_rep, 'encode_spec_kernelE', None, 40)}
+== per-source-line hot spots of (b), global-table kernel
+{lines(enc_rep, 'encode_spec_gtab_kernelE', 'encode_spec_gtab', 40)}
 """)
+e = encs[0] if encs else None
 tr = {"decode_bytes_per_launch": int(dr + dw),
       "decode_split": {"k4::decode_tile_kernel": {"dram_read": int(dr), "dram_write": int(dw)},
                        "k4::decode_tile_big_kernel": "empty work list in the bench's decode pass (every block fits the small stage)",
                        "k4::decode_rest_kernel": "empty work list"},
-      "encode_bytes_per_launch": int(num(e, 'dram__bytes_read.sum') + num(e, 'dram__bytes_write.sum')) if e else
-      int((num(enc8k, 'dram__bytes_read.sum') + num(enc8k, 'dram__bytes_write.sum')) * 8),
+      "encode_bytes_per_launch": int(enc_total(encs)) if encs else int(enc_total(enc_rows) * 8),
       "source": f"profiles/ncu_{tag}_decode_summary.txt, profiles/ncu_{tag}_encode_summary.txt (ncu --set full of `python bench.py --steps 1 --warmup 3 --no-cpu-baseline`)"}
 json.dump(tr, open('profiles/traffic.json', 'w'), indent=1)
 
