@@ -41,6 +41,8 @@ def lines(rep, kname, envk=None, top=40):
 def num(d, k):
     v, u = d[k]
     v = float(v.replace(',', ''))
+    if v != v:                      # ncu prints -nan for a counter it could not collect on a launch
+        return 0.0
     return v * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1}.get(u, 1)
 
 
@@ -79,8 +81,8 @@ open(f'profiles/ncu_{tag}_decode_summary.txt', 'w').write(f"""# ncu --set full -
 enc_rows = raw(enc_rep)
 enc_total = lambda rows: sum(num(d, 'dram__bytes_read.sum') + num(d, 'dram__bytes_write.sum') for d in rows)
 open(f'profiles/ncu_{tag}_encode_summary.txt', 'w').write(f"""# The encoder is two persistent kernels that pull blocks from one device counter and normally run SIDE BY SIDE
-# (encode_spec_gtab_kernel: hash tables in an L2-resident workspace, 25 one-warp CTAs per SM; encode_spec_kernel: hash tables
-# in shared memory, 7 one-warp CTAs per SM).  ncu serialises kernels, so under the profiler the kernel that is launched first
+# (encode_spec_gtab_kernel: hash tables in a global-memory workspace, 22 one-warp CTAs per SM; encode_spec_kernel: hash tables
+# in shared memory, 8 one-warp CTAs per SM).  ncu serialises kernels, so under the profiler the kernel that is launched first
 # (gtab) encodes every block but the last wave and the other one gets the rest: the per-kernel counters below are valid per
 # kernel, the split of the work between them is not what an unprofiled run does.
 
@@ -92,9 +94,13 @@ open(f'profiles/ncu_{tag}_encode_summary.txt', 'w').write(f"""# The encoder is t
 {chr(10).join(fmt(e) + chr(10) for e in enc_rows)}
 
    One warp per block; ~290 warp instructions per sequence on a serial chain of dependent memory round trips (position ->
-   slot -> candidate bytes -> count), so throughput = blocks in flight / latency: 32 one-warp CTAs per SM (the CTA limit, 64
-   registers each).  Only 7 of them keep their table in shared memory -- the rest of the 256 KiB stays L1, which the input
-   windows need more than the tables need shared memory (sweep in DESIGN.md 4.2).
+   slot -> candidate bytes -> count), so throughput = blocks in flight / latency: 30 one-warp CTAs per SM.  Only 8 of them
+   keep their table in shared memory -- the rest of the 256 KiB stays L1, which the input windows need more than the tables
+   need shared memory (sweep in DESIGN.md 7.2).  (-nan rows: ncu could not collect counters on that short launch.)
+   DRAM traffic: 107 GB per pass against 6.75 GB algorithmic.  4 440 blocks are in flight, each with a 64 KiB input window
+   that its match candidates address at random plus a 16 KiB table: 2.2 x the 126 MB L2, so a third of the candidate reads
+   miss L2 (lts hit 68 %) and fetch a DRAM sector each.  DRAM bandwidth is not the limit (10 % of peak) -- the misses cost
+   latency on the chain; fewer blocks in flight miss less but hide less (14 per SM: 1.08 x traffic, 23.9 GB/s; 30: 39.7 GB/s).
 
 == per-source-line hot spots of (b), global-table kernel
 {lines(enc_rep, 'encode_spec_gtab_kernelE', 'encode_spec_gtab', 40)}

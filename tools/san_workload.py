@@ -11,6 +11,9 @@ import numpy as np
 
 import oracle
 import k4os.compression.lz4_b200 as k4
+if len(sys.argv) > 2 and sys.argv[1] == "--lib":       # another build of the library (e.g. -DK4_DT_NEARSPIN=0)
+    from k4os.compression.lz4_b200 import _native as _N
+    _N.SO_PATH = os.path.abspath(sys.argv[2])
 from tests import inputs
 
 port = oracle.Port()
@@ -25,6 +28,11 @@ for b, e, n in zip(blocks, enc, lens):
     assert (int(n), e) == port.encode(b), len(b)
 dec, dl = k4.batch.decode_batch_host(enc, [len(b) for b in blocks])
 assert dec == blocks
+# more blocks than one round of the shared-memory-table encoder kernel: the global-table kernel takes part
+many = [raw[(i * 37) % (5 * bs):(i * 37) % (5 * bs) + 40 + (i * 13) % 900].tobytes() for i in range(1400)]
+me, ml = k4.batch.encode_batch_host(many)
+for b, e, n in zip(many, me, ml):
+    assert (int(n), e) == port.encode(b), len(b)
 rng = np.random.default_rng(1)
 bad = [inputs.mutate(enc[i % 7], rng) for i in range(40)]
 caps = [len(blocks[i % 7]) for i in range(40)]
