@@ -5,15 +5,18 @@
 // TMA bulk store) and a few KiB of bookkeeping; the compressed stream is read from HBM once, the
 // raw block is written once, nothing else moves.
 //
-//   1. SEGMENTED SPECULATIVE PARSE.  The token chain is the only serial part of LZ4 decoding.
-//      The stream is cut into 256-byte segments, one lane each.  A lane starts walking 384 bytes
-//      BEFORE its segment at an arbitrary byte (LZ4 chains are confluent: a walk started anywhere
-//      falls onto the true chain within a few sequences), notes the first position it reaches
-//      inside its segment (entry) and the first one past it (exit), and counts the sequences and
-//      output bytes in between.  Lane 0 is exact; lane t is right iff entry[t] == exit[t-1];
-//      wrong lanes re-walk from exit[t-1] until every link agrees (typically 0-1 rounds).
+//   1. JUMP TABLE + SEGMENTED SPECULATIVE PARSE.  The token chain is the only serial part of LZ4
+//      decoding.  First every thread computes, for four stream positions at a time, the distance to
+//      the next token IF a token started there (parse_table.cuh; one byte per position, kept in the
+//      still unused output tile).  Then the stream is cut into 80-byte segments, one lane each.  A
+//      lane starts walking some hundred bytes BEFORE its segment at an arbitrary byte (LZ4 chains are
+//      confluent: a walk started anywhere falls onto the true chain within a few sequences) -- a
+//      hop is one byte load and an add --, notes the first position it reaches inside its segment
+//      (entry) and the first one past it (exit), and counts the sequences and output bytes in
+//      between.  Lane 0 is exact; lane t is right iff entry[t] == exit[t-1]; wrong lanes re-walk
+//      from exit[t-1] until every link agrees.
 //   2. BLOCK-WIDE EXCLUSIVE SCAN of the per-segment sequence counts and output sizes gives every
-//      segment its first sequence index and output position; a second walk writes one 32-bit
+//      segment its first sequence index and output position; a second walk (same table) writes one 32-bit
 //      descriptor (tokenPos | outPos << 16) per sequence into the still unused TAIL of the output
 //      tile.  (A sequence produces >= 4 output bytes and its descriptor is 4 bytes, so the output
 //      front never overtakes the descriptors of sequences that have not been decoded yet.)
@@ -39,6 +42,7 @@
 
 #include "common.cuh"
 #include "decode_generic.cuh"
+#include "parse_table.cuh"
 
 namespace k4 {
 
@@ -100,9 +104,10 @@ struct TileSmem {
     uint32_t nearCnt[2][DT_WARPS];       // per-warp near-match counts, double-buffered by step parity
     alignas(8) unsigned long long bar;
 };
-// While a block is parsed the output tile is empty; its head holds the per-lane sequence records,
-// the region from SEGX_BASE on the per-segment exits (the descriptors later grow down from the end).
-constexpr uint32_t SEGX_BASE = 60 * 1024;
+// While a block is parsed the output tile is empty: it holds the jump table (parse_table.cuh), one byte
+// per stream position at the stage's own alignment; the descriptors later grow down from the tile's end.
+// The per-segment exits of the parse live in nearIv (unused until the steps begin).
+static_assert(sizeof(uint32_t) * DT_K >= sizeof(uint16_t) * DT_THREADS, "exit array fits nearIv");
 
 static_assert(sizeof(TileSmem<STAGE_SMALL>) <= 115712, "two CTAs per SM: (228 KiB - 2 x 1 KiB) / 2");
 static_assert(sizeof(TileSmem<STAGE_BIG>) <= 232448, "one CTA per SM: 227 KiB");
@@ -237,6 +242,26 @@ __device__ __forceinline__ void seq_next(const uint32_t sStg, const int p, const
     bad = last ? (litEnd != n ? 1u : 0u) : (q2 >= n ? 1u : 0u);
 }
 
+// One hop of a walk through the jump table: sJ = shared address of table byte 0 (position 0).  The
+// escape value sends the (rare) exotic sequence through the exact header code.
+__device__ __forceinline__ int jt_hop(const uint32_t sJ, const uint32_t sStg, const int p, const int n) {
+    const uint32_t j = lds8_ro(sJ + (uint32_t)p);
+    if (j != JT_ESC) return p + (int)j;
+    int nx, o; uint32_t b;
+    seq_next(sStg, p, n, nx, o, b);
+    return nx;
+}
+// The same hop for a sequence that counts: also its decoded size and whether it can be part of a clean block.
+__device__ __forceinline__ void jt_seq(const uint32_t sJ, const uint32_t sStg, const int p, const int n,
+                                       int& next, int& outb, uint32_t& bad) {
+    const uint32_t j = lds8_ro(sJ + (uint32_t)p);
+    if (j != JT_ESC) {
+        next = p + (int)j;
+        outb = (int)jt_outbytes(p, j, [&](int q) { return lds8_ro(sStg + (uint32_t)q); });
+        bad = 0u;
+    } else seq_next(sStg, p, n, next, outb, bad);
+}
+
 // ---- copies inside shared memory (all addresses are 32-bit shared addresses) -------------------
 // whole warp, uniform arguments, source and destination do not overlap: destination-aligned
 // 4-byte words built from two aligned source words
@@ -322,37 +347,38 @@ __device__ int tile_decode_block(TileSmem<STAGE>& S, const uint8_t* __restrict__
     __syncthreads();
     DT_PROF(0);
 
-    // ---- 1. segmented speculative parse ------------------------------------------------------------
+    // ---- 1a. jump table: distance to the next token for EVERY stream position (parse_table.cuh) --------
+    const uint32_t sJ = smem_u32(S.tile) + (uint32_t)shift;     // J[p] sits at the stage's alignment: word k <-> word k
+    {
+        const uint32_t sStage0 = smem_u32(S.stage), sTile0 = smem_u32(S.tile);
+        const int nWords = (shift + n + 3) >> 2;
+        auto ld8 = [&](int q) { return lds8_ro(sStg + (uint32_t)q); };
+        for (int k = tid; k < nWords; k += DT_THREADS) {
+            const uint32_t w0 = lds32_ro(sStage0 + 4u * (uint32_t)k), w1 = lds32_ro(sStage0 + 4u * (uint32_t)k + 4u);
+            sts32(sTile0 + 4u * (uint32_t)k, jt_word(w0, w1, 4 * k - shift, n, ld8));
+        }
+    }
+    __syncthreads();
+    DT_PROF(14);
+
+    // ---- 1b. segmented speculative parse ---------------------------------------------------------------
     constexpr int SEG = TileCfg<STAGE>::SEG;
     const int NS = (n + SEG - 1) / SEG;                          // <= DT_THREADS by the caller's size test
     const int segStart = tid * SEG;
     const int segEnd = segStart + SEG < n ? segStart + SEG : n;
-    // per-lane record area in the (still unused) head of the tile: one u16 per sequence of the segment
-    constexpr uint32_t REC_STRIDE = 2u * (SEG / 3 + 3);
-    static_assert(REC_STRIDE * DT_THREADS <= SEGX_BASE, "records must stay below the exit array");
-    const uint32_t sRec = smem_u32(S.tile) + REC_STRIDE * (uint32_t)tid;
-    const uint32_t sExit = smem_u32(S.tile) + SEGX_BASE;          // u16 per segment, read across warps only
+    const uint32_t sExit = smem_u32(S.nearIv);                    // u16 per segment, read across warps only
     uint32_t myEntry = 0, myExit = 0, myCnt = 0, myOut = 0, myBad = 0;
     // walks from p to the end of the lane's segment; counts what starts inside the segment
     auto walk = [&](int p) {
-        uint32_t entry = 0xFFFFFFFFu, cnt = 0, ob = 0, bad = 0;
-        while (p < segStart) {                                   // warm-up: only the position matters
-            int nx, o; uint32_t b;
-            seq_next(sStg, p, n, nx, o, b);
-            p = nx;
-        }
-        entry = (uint32_t)p;                                     // first position >= segStart
+        uint32_t cnt = 0, ob = 0, bad = 0;
+        while (p < segStart) p = jt_hop(sJ, sStg, p, n);         // warm-up: only the position matters
+        myEntry = (uint32_t)p;                                   // first position >= segStart
         while (p < segEnd) {
             int nx, o; uint32_t b;
-            seq_next(sStg, p, n, nx, o, b);
-            // remember the sequence's compressed and decoded length (255 = "too long, decode again"):
-            // pass 2 then is a short prefix loop over these records instead of a second parse
-            const uint32_t cl = (uint32_t)(nx - p), ol = (uint32_t)o;
-            sts16(sRec + 2u * cnt, (cl < 255u ? cl : 255u) | ((ol < 255u ? ol : 255u) << 8));
-            cnt++; ob += ol; bad |= b;
+            jt_seq(sJ, sStg, p, n, nx, o, b);
+            cnt++; ob += (uint32_t)o; bad |= b;
             p = nx;
         }
-        myEntry = entry;
         myExit = (uint32_t)p; myCnt = cnt; myOut = ob; myBad = bad;
     };
     const bool parses = tid < NS;
@@ -409,22 +435,20 @@ __device__ int tile_decode_block(TileSmem<STAGE>& S, const uint8_t* __restrict__
 
     // descriptors: desc[i] = tokenPos | outPos << 16, in the tail of the tile
     const uint32_t sDesc = smem_u32(S.tile) + (uint32_t)(TILE_BYTES + TILE_PAD) - 4u * (uint32_t)N;   // &desc[0]
-    const bool recordsIntact = 4u * (uint32_t)N + REC_STRIDE * (uint32_t)NS <= (uint32_t)(TILE_BYTES + TILE_PAD);
+    // pass 2 walks the jump table again; it stays intact as long as the descriptors do not reach down to it
+    const bool tableIntact = (uint32_t)(shift + n + 4) + 4u * (uint32_t)N <= (uint32_t)(TILE_BYTES + TILE_PAD);
     if (tid < NS) {
         int p = (int)myEntry;
         uint32_t idx = cBase + cInc - cIn;
         int op = (int)(oBase + oInc - oIn);
-        if (recordsIntact) {                                     // the descriptors do not reach down to the records
-            for (uint32_t k = 0; k < cIn; k++) {
-                const uint32_t rec = lds16(sRec + 2u * k);
-                int cl = (int)(rec & 255u), ol = (int)(rec >> 8);
-                if (cl == 255 || ol == 255) {                    // rare: a long sequence, decode it again
-                    int nx, o; uint32_t b;
-                    seq_next(sStg, p, n, nx, o, b);
-                    cl = nx - p; ol = o;
-                }
+        if (tableIntact) {
+            while (p < segEnd) {
+                int nx, o; uint32_t b;
+                jt_seq(sJ, sStg, p, n, nx, o, b);
                 sts32(sDesc + 4u * idx, (uint32_t)p | ((uint32_t)(op < 65535 ? op : 65535) << 16));
-                idx++; p += cl; op += ol;
+                idx++;
+                op += o;
+                p = nx;
             }
         } else {
             while (p < segEnd) {

@@ -24,6 +24,12 @@ constexpr int ENC_FLAG_X32 = 0x100;      // `level` bit: reproduce the 32-bit en
 #endif
 constexpr int ENC_TAG_BYTES = K4_ENC_TAGS ? 8192 : 0;   // one filter byte per u16 slot (encode_tile.cuh)
 constexpr int ENC_SLOT_BYTES = ENC_TABLE_BYTES + ENC_TAG_BYTES;   // shared memory per warp
+// the global-table encoder warps (encode_tile.cuh) filter their candidate reads by a tag: see TAGMODE there
+#ifndef K4_ENC_GTAG
+#define K4_ENC_GTAG 0
+#endif
+constexpr int ENC_GTAG = K4_ENC_GTAG;
+constexpr int ENC_GSLOT_BYTES = ENC_GTAG == 2 ? 2 * ENC_TABLE_BYTES : (ENC_GTAG ? ENC_TABLE_BYTES + ENC_TABLE_BYTES / 2 : ENC_TABLE_BYTES);
 
 struct EncCtx {
     const uint8_t* src;

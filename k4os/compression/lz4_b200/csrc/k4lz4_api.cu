@@ -103,7 +103,7 @@ cudaError_t encode_launch(const uint8_t* srcBase, const int64_t* srcOff, const i
     // finish in one round goes to them alone.
     const bool useG = k4::ENC_GM_WARPS > 0 && n > wave;
     const int gridG = useG ? D->sms * k4::ENC_GM_WARPS : 0;
-    const size_t tabBytes = (size_t)gridG * k4::ENC_SLOT_BYTES;
+    const size_t tabBytes = (size_t)gridG * k4::ENC_GSLOT_BYTES;
     uint8_t* ws = nullptr;
     cudaError_t e = cudaMallocFromPoolAsync((void**)&ws, 256 + tabBytes, D->pool, st);
     if (e != cudaSuccess) return e;

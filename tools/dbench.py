@@ -18,6 +18,7 @@ ap.add_argument("--mp", type=int, default=630)
 ap.add_argument("--data", default="datagen")
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--what", default="decode")
+ap.add_argument("--check", type=int, default=0, help="encode: compare every CHECK-th block with the oracle engine (bit-exact)")
 ap.add_argument("--lib", default=None, help="alternative build of libk4lz4.so (e.g. a -DK4_DT_PROFILE build under scratch/)")
 a = ap.parse_args()
 if a.lib:
@@ -62,6 +63,15 @@ enc(); torch.cuda.synchronize()
 ratio = float(clen.sum()) / (nb * bs)
 if a.what in ("encode", "both"):
     ms, med = timeit(enc, a.reps)
+    if a.check:
+        import oracle
+        eng = oracle.best()
+        hraw = raw.cpu().numpy(); hs = slots.cpu().numpy(); hl = clen.cpu().numpy()
+        nbad = 0
+        for i in range(0, nb, a.check):
+            r, ref = eng.encode(hraw[i * bs:(i + 1) * bs])
+            if r != int(hl[i]) or hs[i * bound:i * bound + r].tobytes() != ref: nbad += 1
+        print(f"   encode check: {len(range(0, nb, a.check))} blocks vs oracle, {nbad} differ", flush=True)
     print(f"encode[{a.data}{a.mp}]: {ms:.3f} ms (median {med:.3f})  {nb*bs/ms/1e6:.1f} GB/s  ratio {ratio:.3f}", flush=True)
 if a.what in ("decode", "both"):
     poff = torch.cumsum(clen.to(torch.int64), 0) - clen.to(torch.int64)
@@ -96,7 +106,7 @@ if a.what in ("decode", "both"):
         fn(C.addressof(v), 1)
         dec(); torch.cuda.synchronize()
         fn(C.addressof(v), 1)
-        names = ["load", "pass1", "validate", "scan", "pass2", "hdr", "lit", "far", "bar1", "nearlist", "nearwork", "nearbar", "endbar", "store"]
+        names = ["load", "pass1", "validate", "scan", "pass2", "hdr", "lit", "far", "bar1", "nearlist", "nearwork", "nearbar", "endbar", "store", "table"]
         nblk = max(int(v[20]), 1)
         prof = {nm: round(int(v[i]) / nblk) for i, nm in enumerate(names)}
         prof["total"] = sum(prof.values())
