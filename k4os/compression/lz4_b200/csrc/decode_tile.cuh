@@ -61,6 +61,9 @@ constexpr int DT_WARM = K4_DT_WARM;      // speculative warm-up before the segme
 #ifndef K4_DT_NEARSPIN
 #define K4_DT_NEARSPIN 1
 #endif
+#ifndef K4_DT_LATEBAR
+#define K4_DT_LATEBAR 1                    // the barrier that ends a step sits behind the NEXT step's literal copies
+#endif
 #ifndef K4_DT_LSHORT
 #define K4_DT_LSHORT 32
 #endif
@@ -251,15 +254,35 @@ __device__ __forceinline__ int jt_hop(const uint32_t sJ, const uint32_t sStg, co
     seq_next(sStg, p, n, nx, o, b);
     return nx;
 }
-// The same hop for a sequence that counts: also its decoded size and whether it can be part of a clean block.
-__device__ __forceinline__ void jt_seq(const uint32_t sJ, const uint32_t sStg, const int p, const int n,
-                                       int& next, int& outb, uint32_t& bad) {
-    const uint32_t j = lds8_ro(sJ + (uint32_t)p);
-    if (j != JT_ESC) {
-        next = p + (int)j;
-        outb = (int)jt_outbytes(p, j, [&](int q) { return lds8_ro(sStg + (uint32_t)q); });
-        bad = 0u;
-    } else seq_next(sStg, p, n, next, outb, bad);
+// Walks the sequences whose tokens sit in [p, end) and calls f(position, decoded size) for each; returns the
+// first token position >= end and ORs `bad`.  The only serial dependency is table byte -> next position
+// -> table byte: the loads that give a sequence's decoded size are issued BEHIND the next table load and
+// consumed one hop later, so a hop costs one shared-memory round trip (the kernel keeps the LSU queue
+// busy: a dependent load takes hundreds of cycles there, profiles/ncu_r02b_*).
+template <class F>
+__device__ __forceinline__ int jt_walk(const uint32_t sJ, const uint32_t sStg, int p, const int end, const int n,
+                                       uint32_t& bad, F f) {
+    uint32_t j = p < end ? lds8_ro(sJ + (uint32_t)p) : 0u;
+    while (p < end) {
+        int nx, o;
+        uint32_t jn;
+        if (j != JT_ESC) {
+            nx = p + (int)j;
+            const uint32_t tok = lds8_ro(sStg + (uint32_t)p), e1 = lds8_ro(sStg + (uint32_t)p + 1u);
+            const uint32_t m1 = lds8_ro(sStg + (uint32_t)nx - 1u);
+            jn = nx < end ? lds8_ro(sJ + (uint32_t)nx) : 0u;
+            const uint32_t L = tok >> 4, M = tok & 15u;
+            o = (int)(L + M + 4u + (L == 15u ? e1 : 0u) + (M == 15u ? m1 : 0u));      // == jt_outbytes(p, j)
+        } else {
+            uint32_t b;
+            seq_next(sStg, p, n, nx, o, b);
+            bad |= b;
+            jn = nx < end ? lds8_ro(sJ + (uint32_t)nx) : 0u;
+        }
+        f(p, o);
+        p = nx; j = jn;
+    }
+    return p;
 }
 
 // ---- copies inside shared memory (all addresses are 32-bit shared addresses) -------------------
@@ -373,12 +396,7 @@ __device__ int tile_decode_block(TileSmem<STAGE>& S, const uint8_t* __restrict__
         uint32_t cnt = 0, ob = 0, bad = 0;
         while (p < segStart) p = jt_hop(sJ, sStg, p, n);         // warm-up: only the position matters
         myEntry = (uint32_t)p;                                   // first position >= segStart
-        while (p < segEnd) {
-            int nx, o; uint32_t b;
-            jt_seq(sJ, sStg, p, n, nx, o, b);
-            cnt++; ob += (uint32_t)o; bad |= b;
-            p = nx;
-        }
+        p = jt_walk(sJ, sStg, p, segEnd, n, bad, [&](int, int o) { cnt++; ob += (uint32_t)o; });
         myExit = (uint32_t)p; myCnt = cnt; myOut = ob; myBad = bad;
     };
     const bool parses = tid < NS;
@@ -387,8 +405,7 @@ __device__ int tile_decode_block(TileSmem<STAGE>& S, const uint8_t* __restrict__
     // wrong lanes (a literal run that covers several whole segments makes every one of them wrong) is
     // repaired without leaving the warp; across warps through the exit array, one CTA round per hop.
     for (int round = 0;; round++) {
-        __syncthreads();
-        if (round == 0) DT_PROF(1);
+        if (round == 0) { __syncthreads(); DT_PROF(1); }         // later rounds: the barrier that ended the previous round
         bool walked = false;
         for (int it = 0; it < 34; it++) {
             uint32_t e = __shfl_up_sync(FULL, myExit, 1);
@@ -442,14 +459,12 @@ __device__ int tile_decode_block(TileSmem<STAGE>& S, const uint8_t* __restrict__
         uint32_t idx = cBase + cInc - cIn;
         int op = (int)(oBase + oInc - oIn);
         if (tableIntact) {
-            while (p < segEnd) {
-                int nx, o; uint32_t b;
-                jt_seq(sJ, sStg, p, n, nx, o, b);
-                sts32(sDesc + 4u * idx, (uint32_t)p | ((uint32_t)(op < 65535 ? op : 65535) << 16));
+            uint32_t b = 0;
+            jt_walk(sJ, sStg, p, segEnd, n, b, [&](int q, int o) {
+                sts32(sDesc + 4u * idx, (uint32_t)q | ((uint32_t)(op < 65535 ? op : 65535) << 16));
                 idx++;
                 op += o;
-                p = nx;
-            }
+            });
         } else {
             while (p < segEnd) {
                 int nx, o; uint32_t b;
@@ -511,6 +526,14 @@ __device__ int tile_decode_block(TileSmem<STAGE>& S, const uint8_t* __restrict__
             warp_copy(sT + (uint32_t)__shfl_sync(FULL, op, l), sStg + (uint32_t)__shfl_sync(FULL, litPos, l), __shfl_sync(FULL, lit, l), lane);
         }
         DT_PROF(6);
+#if K4_DT_LATEBAR
+        // The previous step's near matches must be final before a far match may read them -- but not before this
+        // step's headers and literals (stage -> bytes beyond everything earlier steps write): warps that are
+        // done with the near phase early do those instead of waiting (the step-end barrier was 17 % of all
+        // warp stall samples).  The near arrays are first touched behind barrier #1 below.
+        if (r > 0) __syncthreads();
+        DT_PROF(11);
+#endif
         lanes_copy(sT + (uint32_t)d, sT + (uint32_t)a, farM && ml <= DT_LSHORT ? ml : 0, off < ml);
         for (unsigned m = __ballot_sync(FULL, farM && ml > DT_LSHORT); m; m &= m - 1) {
             const int l = __ffs(m) - 1;
@@ -597,7 +620,7 @@ __device__ int tile_decode_block(TileSmem<STAGE>& S, const uint8_t* __restrict__
                 if (round > DT_K + 2) return -1;                 // cannot happen: each round retires the first pending match
 #endif
             }
-#if K4_DT_NEARSPIN
+#if K4_DT_NEARSPIN && !K4_DT_LATEBAR
             __syncthreads();
             DT_PROF(11);
 #endif
