@@ -43,6 +43,7 @@
 #include "common.cuh"
 #include "decode_generic.cuh"
 #include "parse_table.cuh"
+#include "lane_copy.cuh"
 
 namespace k4 {
 
@@ -326,8 +327,24 @@ __device__ __forceinline__ void warp_copy_match_smem(uint32_t d, const int off, 
 // loads back to back and only then its stores, so a tier costs one shared-memory round trip instead of
 // one per group of bytes (measured: the byte-group loop was the longest serial chain of a step).
 // `ovl` lanes (LZ77 copy whose source runs into its destination) are done byte by byte afterwards.
+#ifndef K4_DT_WORDCOPY
+#define K4_DT_WORDCOPY 0                   // 1: lane_copy.cuh (4-byte words) instead of byte tiers
+#endif
+struct SmemOps {
+    __device__ __forceinline__ uint32_t ld8(uint32_t a) const { return lds8(a); }
+    __device__ __forceinline__ uint32_t ld32(uint32_t a) const { return lds32(a); }
+    __device__ __forceinline__ void st8(uint32_t a, uint32_t v) const { sts8(a, v); }
+    __device__ __forceinline__ void st32(uint32_t a, uint32_t v) const { sts32(a, v); }
+};
 __device__ __forceinline__ void lanes_copy(const uint32_t d, const uint32_t s, const int len, const bool ovl) {
     const int plain = ovl ? 0 : len;
+#if K4_DT_WORDCOPY
+    static_assert(DT_LSHORT <= LC_MAX, "lane copies are bounded by LC_MAX");
+    SmemOps m;
+    lc_copy(m, d, s, plain, __reduce_max_sync(FULL, lc_words(d, plain)));
+    if (ovl) for (int j = 0; j < len; j++) sts8(d + j, lds8(s + j));
+    return;
+#endif
     const int top = __reduce_max_sync(FULL, plain);
     for (int base = 0; base < top; base += 8) {
         const int left = plain - base;

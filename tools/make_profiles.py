@@ -46,6 +46,53 @@ def num(d, k):
     return v * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1}.get(u, 1)
 
 
+def stalls(d):
+    """warp-state sampling of one kernel: share of every stall reason (all samples)"""
+    pre = 'smsp__pcsamp_warps_issue_stalled_'
+    v = {k[len(pre):]: num(d, k) for k in d if k.startswith(pre) and not k.endswith('_not_issued')}
+    tot = sum(v.values()) or 1.0
+    return "\n".join(f"  {k:24s} {100 * x / tot:5.1f} %" for k, x in sorted(v.items(), key=lambda kv: -kv[1]) if x / tot >= 0.005)
+
+
+def barrier_sites(rep, kregex):
+    """stall_barrier samples per barrier of the kernel (attributed to the instruction behind the BAR)"""
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kregex],
+                         capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    his = [i for i, r in enumerate(rows) if "Instructions Executed" in r]
+    hi, end = his[0], (his[1] - 1 if len(his) > 1 else len(rows))      # the first captured launch of the kernel
+    col = {h: i for i, h in enumerate(rows[hi])}
+    sass = [r for r in rows[hi + 1:end] if len(r) > col['Instructions Executed'] and r[col['Instructions Executed']].isdigit()]
+    import re, tempfile
+    tmp = tempfile.mkdtemp()
+    subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(LIB)], cwd=tmp, capture_output=True)
+    cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+    dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
+    start = [i for i, l in enumerate(dis) if l.startswith(".text.") and "decode_tile_kernelE" in l][0]
+    lines, cur = [], 0
+    for l in dis[start + 1:]:
+        if l.startswith("//---") or l.strip().startswith(".section"):
+            if lines:
+                break
+        m = re.match(r'\s*//## File "(.*)", line (\d+)(.*)', l)
+        if m:
+            cur = (os.path.basename(m.group(1)), int(m.group(2)))
+            continue
+        if re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(.*?);", l):
+            lines.append(cur)
+    tot = sum(int(r[col['# Samples']] or 0) for r in sass)
+    src = open("k4os/compression/lz4_b200/csrc/decode_tile.cuh").read().splitlines()
+    site, last_bar = {}, None
+    for loc, r in zip(lines, sass):
+        if 'BAR.' in r[col['Source']] and loc and loc[0] == 'decode_tile.cuh':
+            last_bar = loc[1]
+        sb = int(r[col['stall_barrier']] or 0)
+        if sb and last_bar:
+            site[last_bar] = site.get(last_bar, 0) + sb
+    return "\n".join(f"  {100 * v / tot:5.1f} % of all samples | decode_tile.cuh:{ln} | {src[ln - 1].strip()[:100]}"
+                     for ln, v in sorted(site.items(), key=lambda kv: -kv[1]) if v / tot >= 0.003)
+
+
 ks = raw(step_rep)
 dec = [d for d in ks if d['Kernel Name'][0].startswith('decode_tile_kernel')][0]
 big = [d for d in ks if d['Kernel Name'][0].startswith('decode_tile_big')]
@@ -65,8 +112,16 @@ open(f'profiles/ncu_{tag}_decode_summary.txt', 'w').write(f"""# ncu --set full -
    (compressed read + raw written) are printed by bench.py as roofline.algorithmic_bytes_per_launch (6 451 287 933 for this config):
    ratio {(dr+dw)/6451287933:.3f} -- the compressed stream is read once, the raw block written once, nothing else moves
    (round 1: 10.1 GB per step = 1.57 x, plus a 4.4 GB scratch allocation).
-   {inst/1e9:.2f} G warp instructions / {nblk} blocks = {inst/nblk/1e3:.0f} K per block.  The kernel is bound by the per-block LATENCY
-   (two blocks resident per SM, shared memory): see DESIGN.md section 7.
+   {inst/1e9:.2f} G warp instructions / {nblk} blocks = {inst/nblk/1e3:.0f} K per block (first capture of round 2: 175 K).  The kernel is
+   bound by the per-block LATENCY (two blocks resident per SM, shared memory): see DESIGN.md section 7.
+
+== warp-state sampling of the tile kernel: where the resident warps spend their cycles
+{stalls(dec)}
+   Half of all warp samples sit at a CTA barrier: the phases of a block have very different amounts of
+   parallelism (parse repair: a few lanes; near matches: dependency chains) and only two blocks fit an SM, so
+   there is little other work to issue meanwhile (issue slots 52 % busy, shared-memory pipe ~40 %).
+   Barrier samples per barrier:
+{barrier_sites(step_rep, '^decode_tile_kernel')}
 
 == launch 2: big-stage variant
 {fmt(big[0]) if big else '  (not captured)'}
@@ -93,14 +148,18 @@ open(f'profiles/ncu_{tag}_encode_summary.txt', 'w').write(f"""# The encoder is t
 #   python tools/dbench.py --blocks 8192 --data datagen --mp 550 --reps 1 --what encode     (1/8 of the pass; source counters)
 {chr(10).join(fmt(e) + chr(10) for e in enc_rows)}
 
-   One warp per block; ~290 warp instructions per sequence on a serial chain of dependent memory round trips (position ->
-   slot -> candidate bytes -> count), so throughput = blocks in flight / latency: 30 one-warp CTAs per SM.  Only 8 of them
-   keep their table in shared memory -- the rest of the 256 KiB stays L1, which the input windows need more than the tables
-   need shared memory (sweep in DESIGN.md 7.2).  (-nan rows: ncu could not collect counters on that short launch.)
-   DRAM traffic: 107 GB per pass against 6.75 GB algorithmic.  4 440 blocks are in flight, each with a 64 KiB input window
-   that its match candidates address at random plus a 16 KiB table: 2.2 x the 126 MB L2, so a third of the candidate reads
-   miss L2 (lts hit 68 %) and fetch a DRAM sector each.  DRAM bandwidth is not the limit (10 % of peak) -- the misses cost
-   latency on the chain; fewer blocks in flight miss less but hide less (14 per SM: 1.08 x traffic, 23.9 GB/s; 30: 39.7 GB/s).
+   One warp per block; ~290 warp instructions per sequence on a serial chain (position -> slot -> candidate bytes ->
+   count), so throughput = blocks in flight / latency: 30 one-warp CTAs per SM.  Only 8 of them keep their table in
+   shared memory -- the rest of the 256 KiB stays L1, which the input windows need more than the tables need shared
+   memory (sweep in DESIGN.md 7.2).  (-nan rows: ncu could not collect counters on that short launch.)
+   The global-table warps use 32-bit slots (position | 16-bit tag): a probe fetches its candidate's bytes only when
+   the tags agree, which removes the 32 scattered window reads per batch -- and doubles the table workspace to
+   148 x 22 x 32 KiB = 104 MB.  DRAM traffic per pass is now 155 GB (16-bit slots: 107 GB) against 6.75 GB
+   algorithmic, L2 hit rate 59 %: the tables no longer fit the 126 MB L2 beside the input windows.  It is still
+   3 % faster, and none of the memory-side experiments moved the encoder by more than that (DESIGN.md 7.2: tag
+   filters in three layouts, candidate / input prefetch, L2 evict-last hints for the tables, evict-first for the
+   input, count loads overlapped with the catch-up): DRAM is at 18 % of its bandwidth, L2 at < 20 %, issue slots
+   at 40 %.  What binds is the length of the dependent instruction chain of ONE warp per sequence.
 
 == per-source-line hot spots of (b), global-table kernel
 {lines(enc_rep, 'encode_spec_gtab_kernelE', 'encode_spec_gtab', 40)}
