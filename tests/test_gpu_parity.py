@@ -626,3 +626,56 @@ def test_frame_container_interoperates_with_upstream(k4):
     got = F.xxh32_batch(base, np.arange(5) * 65536, np.array([65536, 65535, 17, 3, 0], dtype=np.int32), 9)
     want = [port.xxh32(np.frombuffer(b[:n], dtype=np.uint8), 9) for b, n in zip(blocks, [65536, 65535, 17, 3, 0])]
     assert got.tolist() == want
+
+
+def test_jump_table_edge_streams_gpu(k4):
+    """Streams aimed at the boundaries of the parse's jump table (csrc/parse_table.cuh): literal-length
+    extension bytes 222..255 and chains of them, match-length extension bytes 253..255 and chains, sequences
+    that end exactly at / one before / one behind the end of the stream, all packed back to back so that
+    every stage alignment occurs.  Return codes and bytes must equal the oracle's."""
+    import oracle
+    port = oracle.Port()
+    rng = np.random.default_rng(5)
+    streams, caps = [], []
+
+    def seq(lit, mlen, off, last=False):
+        """one hand-assembled sequence: `lit` literal bytes, then (unless last) a match of mlen >= 4 at distance off"""
+        out = bytearray()
+        lt = min(lit, 15)
+        mt = 0 if last else min(mlen - 4, 15)
+        out.append((lt << 4) | mt)
+        if lit >= 15:
+            rest = lit - 15
+            out += b"\xFF" * (rest // 255) + bytes([rest % 255])
+        out += rng.integers(1, 255, lit, dtype=np.uint8).tobytes()
+        if not last:
+            out += bytes([off & 0xFF, off >> 8])
+            if mlen - 4 >= 15:
+                rest = mlen - 4 - 15
+                out += b"\xFF" * (rest // 255) + bytes([rest % 255])
+        return bytes(out)
+
+    for lit in (14, 15, 16, 15 + 222, 15 + 223, 15 + 224, 15 + 254, 15 + 255, 15 + 256, 15 + 510, 15 + 511, 900):
+        for mlen in (4, 18, 19, 20, 19 + 253, 19 + 254, 19 + 255, 19 + 256, 19 + 510, 19 + 765, 3000):
+            body = seq(40, 8, 7) + seq(lit, mlen, 5) + seq(3, 6, 2) + seq(12, 0, 0, last=True)
+            total = 40 + 8 + lit + mlen + 3 + 6 + 12
+            for cut in (0, 1, 2, 5):            # truncated tails: the last sequences end at / behind the end
+                s = body[:len(body) - cut] if cut else body
+                streams.append(s); caps.append(total + 20)
+            streams.append(body + b"\x00"); caps.append(total + 20)          # one byte behind a complete block
+    # the same shapes at the far end of long valid blocks (table entries near n, big distances)
+    for n in (5000, 33000, 65536):
+        base = port.encode(inputs.gen("text2", n, n))[1]
+        for tail in (seq(15 + 224, 19 + 255, 9) + seq(9, 0, 0, last=True), seq(300, 600, 300) + seq(5, 0, 0, last=True)):
+            # a valid block is token-complete: append more sequences by re-opening its terminal literal run is not
+            # possible in general, so just check the concatenation is handled like the oracle handles it
+            streams.append(base + tail); caps.append(70000)
+    dec, got = k4.batch.decode_batch_host(streams, caps)
+    n_ok = 0
+    for i, (c, cap) in enumerate(zip(streams, caps)):
+        r, ref = port.decode(c, cap)
+        assert int(got[i]) == r, (i, len(c), cap, int(got[i]), r)
+        if r > 0 and not inputs.uses_zero_offset(c):
+            assert dec[i] == ref, i
+            n_ok += 1
+    assert n_ok >= 100, n_ok       # the complete hand-assembled blocks decode
