@@ -161,6 +161,8 @@ open(f'profiles/ncu_{tag}_encode_summary.txt', 'w').write(f"""# The encoder is t
    input, count loads overlapped with the catch-up): DRAM is at 18 % of its bandwidth, L2 at < 20 %, issue slots
    at 40 %.  What binds is the length of the dependent instruction chain of ONE warp per sequence.
 
+== warp-state sampling of (b): share of the stall reasons, global-table kernel then shared-memory-table kernel
+{chr(10).join(stalls(e) + chr(10) for e in enc_rows)}
 == per-source-line hot spots of (b), global-table kernel
 {lines(enc_rep, 'encode_spec_gtab_kernelE', 'encode_spec_gtab', 40)}
 """)
