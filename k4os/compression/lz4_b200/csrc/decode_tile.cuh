@@ -94,7 +94,11 @@ __device__ unsigned long long g_decode_prof[32];
 
 // Parse-lane granularity: every one of the 512 threads parses, so the serial chain per lane is as
 // short as the stage allows (40 KiB / 512 = 80 bytes; 64 KiB / 512 = 128 bytes).
-template <int STAGE> struct TileCfg { static constexpr int SEG = STAGE <= 40 * 1024 ? 80 : 128; };
+#ifndef K4_DT_SEG
+#define K4_DT_SEG 80
+#endif
+template <int STAGE> struct TileCfg { static constexpr int SEG = STAGE <= 40 * 1024 ? K4_DT_SEG : 128; };
+static_assert(K4_DT_SEG * K4_DT_THREADS >= 40 * 1024 && K4_DT_SEG <= 128, "one lane per segment of the small stage");
 
 template <int STAGE>
 struct TileSmem {
@@ -626,7 +630,10 @@ __device__ int tile_decode_block(TileSmem<STAGE>& S, const uint8_t* __restrict__
                 // index (same warp, lower lane, or an earlier warp), entry 0 waits for nothing, so polling
                 // the flags terminates; one barrier after the loop publishes the step
                 if (!warpHasWork || !__any_sync(FULL, pend)) break;
-                __nanosleep(40);
+#ifndef K4_DT_SPINNS
+#define K4_DT_SPINNS 40
+#endif
+                __nanosleep(K4_DT_SPINNS);
                 DT_PROF_COUNT(18, 1);
                 if (round > (1 << 20)) break;                     // (bounded for safety; never reached)
 #else
